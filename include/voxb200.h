@@ -1,0 +1,182 @@
+/*
+ * voxb200.h -- C ABI of libvoxb200.so: the B200-native chunk-production path
+ * for Blatko1/wgpu-voxel-engine (noise terrain fill -> hidden-face culling /
+ * instance emission -> per-chunk frustum AABB test).
+ *
+ * This is the drop-in boundary.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference's src/).  The Rust
+ * FFI crate that binds these symbols is in wgpu-voxel-engine_b200/rust/ and is
+ * walked through in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every call returns an int status: 0 = VX_OK, negative = error; the text
+ *     of the last error on the calling thread is vx_last_error().  The
+ *     reference has no error path here (it panics, chunk_builder.rs:83,107,128);
+ *     the Rust shim panics on non-zero.
+ *   - all outputs are caller-allocated; the library never frees caller memory.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails
+ *     with VX_ERR_NO_DEVICE.
+ *   - calls on one context are serialised (thread-safe); use one context per
+ *     calling thread / GPU for concurrency.
+ *   - chunk edge is fixed at 32 (world.rs:21); voxel index inside a chunk is
+ *     idx = x + 32*z + 1024*y (chunk.rs:38,70); chunk -> world is a wrapping
+ *     i32 multiply by 32 (coordinate.rs:60-65, release-build semantics).
+ */
+#ifndef VOXB200_H
+#define VOXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_VERSION 100          /* 0.1.0 */
+#define VX_CHUNK 32
+#define VX_VOXELS 32768
+#define VX_ROWS 1024            /* occupancy words per chunk: row = y*32+z, bit = x */
+#define VX_MAX_QUADS_PER_CHUNK 98304
+#define VX_MAX_OCTAVES 8
+
+enum {
+    VX_OK = 0,
+    VX_ERR_BAD_ARG = -1,
+    VX_ERR_CAPACITY = -2,       /* instance buffer too small; counts/offsets/total are valid */
+    VX_ERR_CUDA = -3,
+    VX_ERR_NO_DEVICE = -4,
+    VX_ERR_OOM = -5,
+    VX_ERR_BAD_BLOCK = -6       /* a block id outside {0,1,2} (cube.rs:16-21) */
+};
+
+/* cube.rs:16-21 CubeType */
+enum { VX_GRASS = 0, VX_DIRT = 1, VX_AIR = 2 };
+/* per-cube emission order of chunk.rs:77-240 */
+enum { VX_LEFT = 0, VX_RIGHT = 1, VX_BACK = 2, VX_FRONT = 3, VX_DOWN = 4, VX_UP = 5 };
+
+/* perlin_noise.rs:14-18 -- the reference hard-codes these; the defaults
+ * (vx_default_noise_params) reproduce them. */
+typedef struct vx_noise_params {
+    int32_t seed;        /* 1    */
+    float freq;          /* 0.09 */
+    float gain;          /* 2.5  */
+    float lacunarity;    /* 0.5  */
+    int32_t octaves;     /* 3 (1..VX_MAX_OCTAVES) */
+} vx_noise_params;
+
+/* renderer/instance.rs:1-6 InstanceRaw, #[repr(C)]: 16 f32 + u32 = 68 bytes.
+ * t_matrix[c] is column c of Translation(pos) * Rotation(face) (quad.rs:47-54). */
+typedef struct vx_instance {
+    float t_matrix[4][4];
+    uint32_t texture_index;
+} vx_instance;
+
+typedef struct vx_ctx vx_ctx;
+
+/* ---- library / context -------------------------------------------------- */
+int vx_version(void);
+const char *vx_last_error(void);
+/* number of CUDA devices, or a negative status */
+int vx_device_count(void);
+/* devices == NULL: use n_devices devices starting at 0 (n_devices <= 0: all).
+ * With several devices every batch call shards its list by contiguous index
+ * ranges, one stream per GPU, no inter-GPU traffic (halo slabs are recomputed). */
+int vx_create(const int *devices, int n_devices, vx_ctx **out);
+void vx_destroy(vx_ctx *ctx);
+int vx_num_devices(const vx_ctx *ctx);
+void vx_default_noise_params(vx_noise_params *p);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t vx_launch_count(const vx_ctx *ctx);
+/* pinned host memory for the host-buffer entry points (optional but faster) */
+int vx_host_alloc(void **out, size_t bytes);
+int vx_host_free(void *p);
+
+/* ---- terrain fill -------------------------------------------------------
+ * Replaces Chunk::new / Chunk::generate_terrain (chunk.rs:21-46) and
+ * perlin_noise::perlin_3d_block_{avx2,sse41} (perlin_noise.rs:5-41).
+ * coords: int32[n][3] chunk coordinates (ChunkCoord3D, coordinate.rs:41-46).
+ * Any output may be NULL:
+ *   blocks_out     uint8 [n][32768]  CubeType per voxel (Vec<Cube>, chunk.rs:17)
+ *   noise_out      float [n][32768]  the f32 noise field (perlin_noise.rs:20)
+ *   occupancy_out  uint32[n][1024]   bit x of word y*32+z set <=> voxel != AIR
+ *   near_zero_out  uint64[1]         voxels with |noise| <= 1e-6 (tolerance census) */
+int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+            uint8_t *blocks_out, float *noise_out, uint32_t *occupancy_out,
+            uint64_t *near_zero_out);
+
+/* ---- meshing of caller-provided block grids -----------------------------
+ * Replaces Chunk::create_mesh / cull_unseen_triangles / ChunkMesh::new
+ * (chunk.rs:48-57, 59-245, 254-266) minus the wgpu upload.
+ * blocks: uint8[n][32768].  nbr_idx: int32[n][4] = index into this list of the
+ * -x,+x,-z,+z neighbour (order of chunk_builder.rs:134-169) or -1 for None;
+ * NULL = look neighbours up by coordinate inside the list.  mesh_mask: uint8[n],
+ * 0 = the chunk only serves as a neighbour (count 0); NULL = mesh all.
+ * Outputs: counts uint32[n], offsets uint64[n+1] (exclusive scan of counts),
+ * instances[capacity] in list order, each chunk's quads in the reference's
+ * emission order ((y,z,x)-major, then LEFT,RIGHT,BACK,FRONT,DOWN,UP).
+ * instances may be NULL (count only).  total_out receives offsets[n]. */
+int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
+            const int32_t *nbr_idx, const uint8_t *mesh_mask,
+            uint32_t *counts, uint64_t *offsets,
+            vx_instance *instances, size_t capacity, uint64_t *total_out);
+
+/* ---- fused generate + mesh ----------------------------------------------
+ * The worker closure of chunk_builder.rs:80-84 (Chunk::new then create_mesh)
+ * over a coordinate list.  nbr_mask: uint8[n], bit k set = neighbour k is
+ * present (its blocks come from the same noise, wherever it is); NULL =
+ * present iff the neighbour coordinate is in the list.  blocks_out optional. */
+int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                const uint8_t *nbr_mask,
+                uint32_t *counts, uint64_t *offsets,
+                vx_instance *instances, size_t capacity, uint64_t *total_out,
+                uint8_t *blocks_out);
+
+/* ---- frustum -------------------------------------------------------------
+ * vx_planes_from_matrix replaces Frustum::matrix_to_planes
+ * (frustum_culling.rs:47-85): m = column-major Matrix4<f32> (m[c*4+r]),
+ * planes[6][4] in the stored order near, far, left, right, top, bottom.
+ * vx_frustum_cull replaces Frustum::contains (frustum_culling.rs:16-40) for
+ * n chunks x n_frames plane sets: visible[f*n + i] = 1 iff ANY of the 8 AABB
+ * corners of chunk i is inside ALL six planes of frame f. */
+int vx_planes_from_matrix(const float m[16], float planes[24]);
+int vx_frustum_cull(vx_ctx *ctx, const float *planes, size_t n_frames,
+                    const int32_t *coords, size_t n, uint8_t *visible);
+/* bit-packed result: bits[f*ceil(n/32) + i/32] bit (i%32) */
+int vx_frustum_cull_bits(vx_ctx *ctx, const float *planes, size_t n_frames,
+                         const int32_t *coords, size_t n, uint32_t *bits);
+
+/* ---- device-resident variants --------------------------------------------
+ * Same semantics; every pointer is DEVICE memory on the context's first GPU,
+ * work is enqueued on `stream` (a cudaStream_t, NULL = the context's stream)
+ * and the call returns without synchronising.  Capacity overflow cannot be
+ * reported synchronously: status[0] (device uint32, optional) gets bit 0 set,
+ * bit 1 = bad block id.  Scratch lives in the context and is valid until the
+ * next call on it. */
+int vx_fill_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                   uint8_t *blocks_out, float *noise_out, uint32_t *occupancy_out,
+                   uint64_t *near_zero_out, void *stream);
+int vx_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
+                   const int32_t *nbr_idx, const uint8_t *mesh_mask,
+                   uint32_t *counts, uint64_t *offsets,
+                   vx_instance *instances, size_t capacity, uint32_t *status, void *stream);
+int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                       const uint8_t *nbr_mask,
+                       uint32_t *counts, uint64_t *offsets,
+                       vx_instance *instances, size_t capacity, uint32_t *status,
+                       uint8_t *blocks_out, void *stream);
+int vx_frustum_cull_device(vx_ctx *ctx, const float *planes, size_t n_frames,
+                           const int32_t *coords, size_t n, uint8_t *visible, uint32_t *bits,
+                           void *stream);
+/* block until everything enqueued by this context has finished */
+int vx_sync(vx_ctx *ctx);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------
+ * Measured non-tensor issue peaks of the current device, in Tera-ops/s
+ * (FMA counts 2): kind 0 = FP32 FFMA, 1 = FP32 FMUL+FADD (non-fused),
+ * 2 = INT32 IMAD+LOP3 mix. */
+int vx_measure_peak(vx_ctx *ctx, int kind, double *tera_ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,292 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle and the
+golden vectors.  Bit-exact for blocks, occupancy, quad sequences and frustum
+bits; noise within 1e-6 absolute (north_star) -- in fact bit-exact -- with the
+near-threshold census reported."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(vox):
+    c = vox.Context()
+    yield c
+    c.close()
+
+
+def _neighbours(c):
+    cx, cy, cz = (int(v) for v in c)
+    return [(cx - 1, cy, cz), (cx + 1, cy, cz), (cx, cy, cz - 1), (cx, cy, cz + 1)]
+
+
+def _canon(inst):
+    """Signed zeros of the rotation products are not pinned: compare with -0 == +0."""
+    out = inst.copy()
+    out["t_matrix"] = out["t_matrix"] + np.float32(0)
+    return out
+
+
+COORDS = [(0, 0, 0), (1, 0, 0), (-1, 0, -1), (511, 0, -512), (-16, 0, 15), (7, 1, -3), (0, -2, 0),
+          (100000, 3, -99999)]
+
+
+def test_fill_blocks_noise_bit_exact(ctx, oracle):
+    res = ctx.fill(COORDS, blocks=True, noise=True, occupancy=True, census=True)
+    near = 0
+    for i, c in enumerate(COORDS):
+        want = oracle.noise_chunk(c)
+        got = res["noise"][i]
+        assert float(np.max(np.abs(got - want))) <= 1e-6          # north_star tolerance
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))   # and in fact bit-exact
+        cubes = oracle.terrain_from_noise(want)
+        assert np.array_equal(res["blocks"][i], cubes)
+        bits = np.unpackbits(res["occupancy"][i].view(np.uint8), bitorder="little").reshape(32768)
+        assert np.array_equal(bits.astype(bool), cubes != oracle.AIR)
+        near += int((np.abs(want) <= np.float32(1e-6)).sum())
+    assert res["near_zero"] == near           # tolerance census: counted and reported, not hidden
+    print("near-threshold voxels (|noise| <= 1e-6): %d of %d" % (near, 32768 * len(COORDS)))
+
+
+def test_fill_golden_crc(ctx, golden):
+    recs = golden["chunks"]
+    res = ctx.fill([r["coord"] for r in recs], blocks=True, noise=True, census=False)
+    for i, r in enumerate(recs):
+        assert "%08x" % zlib.crc32(res["blocks"][i].tobytes()) == r["occ_crc32"]
+        assert ["%08x" % int(v) for v in res["noise"][i][::997].view(np.uint32)] == r["noise_sample_997"]
+    # fast kernel variant (no noise output) must give the same blocks
+    res2 = ctx.fill([r["coord"] for r in recs], blocks=True)
+    assert np.array_equal(res2["blocks"], res["blocks"])
+
+
+@pytest.mark.parametrize("seed,octaves,freq", [(2, 3, 0.09), (12345, 1, 0.9), (1, 4, 0.05), (7, 2, 0.09)])
+def test_fill_other_params(ctx, oracle, vox, seed, octaves, freq):
+    p = vox.default_noise_params(seed=seed, octaves=octaves, freq=freq)
+    po = oracle.default_params(seed=seed, octaves=octaves, freq=freq)
+    cs = [(0, 0, 0), (-5, 0, 9)]
+    res = ctx.fill(cs, params=p, noise=True)
+    for i, c in enumerate(cs):
+        want = oracle.noise_chunk(c, po)
+        assert np.array_equal(res["noise"][i].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(res["blocks"][i], oracle.terrain_from_noise(want))
+
+
+@pytest.mark.parametrize("p_solid,p_dirt", [(0.1, 0.0), (0.5, 0.3), (0.9, 0.5)])
+def test_mesh_random_grids_exact_sequence(ctx, oracle, p_solid, p_dirt):
+    rng = np.random.default_rng(int(p_solid * 100))
+    n = 7
+    coords = np.array([(i - 3, rng.integers(-2, 3), 2 * i) for i in range(n)], np.int32)
+    solid = rng.random((n, 32768)) < p_solid
+    dirt = rng.random((n, 32768)) < p_dirt
+    blocks = np.where(solid, np.where(dirt, 1, 0), 2).astype(np.uint8)
+    nbr = rng.integers(-1, n, size=(n, 4)).astype(np.int32)        # arbitrary neighbour wiring, -1 = None
+    got = ctx.mesh(coords, blocks, nbr_idx=nbr)
+    want = oracle.mesh_batch(coords, blocks, nbr)
+    assert np.array_equal(got.counts, want["counts"])
+    assert np.array_equal(got.offsets, want["offsets"])
+    assert got.total == want["total"]
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+
+
+def test_mesh_checkerboard_worst_case(ctx, oracle):
+    g = np.indices((32, 32, 32)).sum(axis=0) & 1
+    cb = np.where(g == 0, 0, 2).astype(np.uint8).reshape(-1)
+    coords = np.array([(0, 0, 0), (1, 0, 0)], np.int32)
+    blocks = np.stack([cb, np.where(g == 1, 1, 2).astype(np.uint8).reshape(-1)])
+    got = ctx.mesh(coords, blocks)                       # neighbours resolved by coordinate
+    assert got.counts.tolist() == [98304, 98304]
+    want = oracle.mesh_batch(coords, blocks, np.array([[-1, 1, -1, -1], [0, -1, -1, -1]], np.int32))
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+
+
+def test_mesh_edge_cases(ctx, vox):
+    empty = ctx.mesh(np.zeros((0, 3), np.int32), np.zeros((0, 32768), np.uint8))
+    assert empty.total == 0 and empty.offsets.tolist() == [0]
+    air = np.full((1, 32768), 2, np.uint8)
+    r = ctx.mesh([(0, 0, 0)], air)
+    assert r.total == 0 and r.counts.tolist() == [0]
+    solid = np.zeros((1, 32768), np.uint8)
+    r = ctx.mesh([(0, 0, 0)], solid)
+    assert r.total == 6 * 1024
+    # mesh_mask = 0: the chunk only serves as a neighbour
+    both = np.zeros((2, 32768), np.uint8)
+    r = ctx.mesh([(0, 0, 0), (1, 0, 0)], both, mesh_mask=[1, 0])
+    assert r.counts.tolist() == [5 * 1024, 0]
+    # capacity overflow is an error, counts stay valid
+    with pytest.raises(vox.VoxError) as e:
+        ctx.mesh([(0, 0, 0)], solid, capacity=100)
+    assert e.value.code == vox._lib.VX_ERR_CAPACITY
+    # a block id outside {0,1,2} is rejected (cube.rs:16-21)
+    bad = solid.copy()
+    bad[0, 777] = 9
+    with pytest.raises(vox.VoxError) as e:
+        ctx.mesh([(0, 0, 0)], bad)
+    assert e.value.code == vox._lib.VX_ERR_BAD_BLOCK
+    with pytest.raises(vox.VoxError):
+        ctx.fill([(0, 0, 0)], params=vox.default_noise_params(octaves=0))
+
+
+def _grid(x0, z0, nx, nz, y=0):
+    return np.array([(x, y, z) for z in range(z0, z0 + nz) for x in range(x0, x0 + nx)], np.int32)
+
+
+def test_gen_mesh_region_in_list_policy(ctx, oracle):
+    coords = _grid(-3, -2, 6, 5)
+    got = ctx.gen_mesh(coords, blocks=True)
+    want = oracle.gen_mesh_batch(coords, want_cubes=True)
+    assert np.array_equal(got.blocks, want["cubes"])
+    assert np.array_equal(got.counts, want["counts"])
+    assert np.array_equal(got.offsets, want["offsets"])
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+
+
+def test_gen_mesh_neighbour_masks_and_halo(ctx, oracle):
+    # neighbours declared present although they are NOT in the list -> halo slabs from noise;
+    # neighbours in the list but masked out -> None (chunk_builder.rs:134-169 snapshots)
+    rng = np.random.default_rng(5)
+    coords = np.array([(0, 0, 0), (1, 0, 0), (5, 0, 5), (-7, 1, 2), (0, 0, 1)], np.int32)
+    masks = rng.integers(0, 16, size=len(coords)).astype(np.uint8)
+    masks[2] = 15
+    got = ctx.gen_mesh(coords, nbr_mask=masks)
+    for i, c in enumerate(coords):
+        cubes = oracle.generate_terrain(c)
+        adj = [oracle.generate_terrain(nc) if (masks[i] >> k) & 1 else None
+               for k, nc in enumerate(_neighbours(c))]
+        want = oracle.create_mesh(c, cubes, adj)
+        assert got.counts[i] == len(want)
+        assert _canon(got.chunk(i)).tobytes() == _canon(want).tobytes()
+
+
+def test_gen_mesh_sharded_equals_whole(ctx):
+    # coordinate sharding: meshing two halves with explicit presence masks
+    # reproduces the whole-region result byte for byte
+    coords = _grid(-4, -4, 8, 8)
+    whole = ctx.gen_mesh(coords)
+    inside = {tuple(c) for c in coords.tolist()}
+    mask = np.array([sum(1 << k for k, nc in enumerate(_neighbours(c)) if nc in inside) for c in coords], np.uint8)
+    a = ctx.gen_mesh(coords[:32], nbr_mask=mask[:32])
+    b = ctx.gen_mesh(coords[32:], nbr_mask=mask[32:])
+    assert np.array_equal(np.concatenate([a.counts, b.counts]), whole.counts)
+    assert a.instances.tobytes() + b.instances.tobytes() == whole.instances.tobytes()
+    again = ctx.gen_mesh(coords)
+    assert again.instances.tobytes() == whole.instances.tobytes()       # deterministic
+
+
+def test_gen_mesh_ring_32x32_properties(ctx, oracle):
+    # BASELINE config 2 at full size: size-independent properties + sampled oracle checks
+    coords = _grid(-16, -16, 32, 32)
+    res = ctx.gen_mesh(coords, blocks=True)
+    assert res.total == int(res.counts.sum()) == int(res.offsets[-1])
+    assert np.array_equal(np.diff(res.offsets.astype(np.int64)), res.counts.astype(np.int64))
+    solid = (res.blocks != 2)
+    inst = res.instances
+    # every instance sits on a solid voxel of its chunk, w row is (0,0,0,1), texture in {0,1,2}
+    assert np.all(inst["t_matrix"][:, 3, 3] == 1.0) and np.all(inst["t_matrix"][:, :3, 3] == 0.0)
+    assert set(np.unique(inst["texture_index"]).tolist()) <= {0, 1, 2}
+    # inside the region, faces between two chunks cancel: #LEFT over all == #RIGHT over all
+    col0 = inst["t_matrix"][:, 0, :3]
+    left = int(np.sum(col0[:, 2] == 1.0) - 0)     # LEFT column 0 = (e, 0, 1)
+    right = int(np.sum(col0[:, 2] == -1.0))       # RIGHT column 0 = (e, 0, -1)
+    assert left == right
+    for i in (0, 31, 500, 1023):
+        c = coords[i]
+        cubes = oracle.generate_terrain(c)
+        assert np.array_equal(res.blocks[i], cubes)
+        inside = {tuple(x) for x in coords.tolist()}
+        adj = [oracle.generate_terrain(nc) if nc in inside else None for nc in _neighbours(c)]
+        want = oracle.create_mesh(c, cubes, adj)
+        assert _canon(res.chunk(i)).tobytes() == _canon(want).tobytes()
+    assert solid.any() and not solid.all()
+
+
+def test_reference_interface_mirror(ctx, vox, oracle):
+    # reads like the reference's call site chunk_builder.rs:80-84
+    pos = vox.ChunkCoord3D(0, 0, 0)
+    data = vox.Chunk.new(pos, ctx)
+    left = vox.Chunk.new(vox.ChunkCoord3D(-1, 0, 0), ctx)
+    front = vox.Chunk.new(vox.ChunkCoord3D(0, 0, 1), ctx)
+    mesh = data.create_mesh(ctx, [left, None, None, front])
+    cubes = oracle.generate_terrain(pos)
+    assert np.array_equal(data.cubes, cubes)
+    want = oracle.create_mesh(pos, cubes, [oracle.generate_terrain((-1, 0, 0)), None, None,
+                                           oracle.generate_terrain((0, 0, 1))])
+    assert mesh.instances_len == len(want)
+    assert _canon(mesh.instance_buffer).tobytes() == _canon(want).tobytes()
+    chunks, meshes = vox.build_chunks([(0, 0, 0), (-1, 0, 0)], ctx)
+    assert np.array_equal(chunks[0].cubes, cubes) and meshes[0].instances_len > 0
+
+
+def test_frustum_golden_and_oracle(ctx, vox, oracle, golden):
+    for fx in golden["frustum"]:
+        m = np.array([int(h, 16) for h in fx["matrix_colmajor"]], np.uint32).view(np.float32)
+        fr = vox.Frustum.new(m, ctx)
+        lo, hi = fx["grid"]
+        g = np.arange(lo, hi, dtype=np.int32)
+        cz, cx = np.meshgrid(g, g, indexing="ij")
+        coords = np.stack([cx.reshape(-1), np.zeros(cx.size, np.int32), cz.reshape(-1)], axis=1)
+        vis = fr.contains_many(coords)
+        assert int(vis.sum()) == fx["visible_count"]
+        assert "%08x" % zlib.crc32(vis.astype(np.uint8).tobytes()) == fx["vis_crc32"]
+        assert fr.contains(tuple(coords[0])) == bool(vis[0])
+
+
+def test_frustum_random_planes_batched(ctx, oracle):
+    rng = np.random.default_rng(11)
+    F, n = 70, 1000                       # > 64 frames (two frame blocks), ragged n
+    planes = rng.standard_normal((F, 6, 4)).astype(np.float32)
+    planes[:, :, 3] += 200.0
+    planes[3, 2, 0] = np.nan              # NaN distance counts as inside (frustum_culling.rs:33)
+    planes[5, :, :] = 0.0
+    coords = rng.integers(-40, 40, size=(n, 3)).astype(np.int32)
+    coords[0] = (1 << 26, 0, -(1 << 26))  # wrapping world coordinates
+    want = oracle.frustum_cull(planes, coords)
+    got = ctx.frustum_cull(planes, coords)
+    assert np.array_equal(got, want)
+    bits = ctx.frustum_cull(planes, coords, bits=True)
+    unpacked = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :n]
+    assert np.array_equal(unpacked, want)
+    assert 0 < want.sum() < want.size
+
+
+def test_device_resident_api(ctx, vox):
+    torch = pytest.importorskip("torch")
+    coords = _grid(-2, -2, 4, 4)
+    host = ctx.gen_mesh(coords)
+    dev = torch.device("cuda:0")
+    n = len(coords)
+    d_coords = torch.from_numpy(coords).to(dev)
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    cap = host.total + 10
+    d_inst = torch.zeros(cap * 17, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.gen_mesh_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_offsets.data_ptr(), d_inst.data_ptr(), cap,
+                        status_ptr=d_status.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    assert d_status[0].item() == 0
+    assert np.array_equal(d_counts.cpu().numpy().view(np.uint32), host.counts)
+    got = d_inst.cpu().numpy().view(np.uint8)[:host.total * 68]
+    assert got.tobytes() == host.instances.tobytes()
+    # overflow is flagged, not written
+    ctx.gen_mesh_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_offsets.data_ptr(), d_inst.data_ptr(), 5,
+                        status_ptr=d_status.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    assert d_status[0].item() & 1
+
+
+def test_multi_gpu_context_equals_single(ctx, vox):
+    if vox._lib.lib().vx_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    coords = _grid(-5, -5, 10, 10)
+    one = ctx.gen_mesh(coords, blocks=True)
+    with vox.Context(n_devices=2) as c2:
+        two = c2.gen_mesh(coords, blocks=True)
+        assert np.array_equal(one.counts, two.counts) and np.array_equal(one.offsets, two.offsets)
+        assert one.instances.tobytes() == two.instances.tobytes()
+        assert np.array_equal(one.blocks, two.blocks)
+        f1 = ctx.fill(coords, noise=True)
+        f2 = c2.fill(coords, noise=True)
+        assert np.array_equal(f1["noise"], f2["noise"])

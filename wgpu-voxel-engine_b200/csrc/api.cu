@@ -1,0 +1,800 @@
+// api.cu -- the extern "C" boundary of libvoxb200.so (include/voxb200.h).
+//
+// Host side of the B200 path: one context owns one or more GPUs; each GPU has
+// a compute stream, a copy stream, grow-only scratch buffers and two instance
+// arenas.  Batch calls shard the coordinate list across the GPUs by contiguous
+// index range with no inter-GPU traffic: a neighbour that lives in another
+// shard (or outside the list but declared present) is a "halo" whose single
+// border slab is regenerated from the noise on the GPU that needs it.
+// Instances stream back through the two arenas (emit slice k+1 overlaps the
+// D2H of slice k).  There is no CPU compute path in this file.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vx_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what, int line)
+{
+    cudaGetLastError();   // clear sticky-less errors
+    return fail(e == cudaErrorMemoryAllocation ? VX_ERR_OOM : VX_ERR_CUDA, "CUDA error %d (%s) at api.cu:%d: %s",
+                (int)e, cudaGetErrorString(e), line, what);
+}
+
+#define CK(expr)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (expr);                                      \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr, __LINE__); \
+    } while (0)
+#define RET(expr)                 \
+    do {                          \
+        int r_ = (expr);          \
+        if (r_ != VX_OK) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);   // implicit device sync: nothing in flight still uses it
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr size_t kArenaBytes = size_t(256) << 20;                      // per instance arena
+constexpr size_t kArenaQuads = kArenaBytes / sizeof(vx_instance);      // >= 98304 (one chunk always fits)
+constexpr size_t kSliceBytes = size_t(256) << 20;                      // staging for fill / frustum outputs
+
+struct Dev {
+    int id = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr, copy = nullptr;
+    cudaEvent_t emit_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_in, counts, offsets, small, blocks, noise,
+        inst[2], planes, vis, bits, mesh_mask;
+    uint32_t *h_small = nullptr;   // pinned mirror of `small`
+    uint64_t launches = 0;
+    // `small` layout (bytes): 0 status u32 | 4 halo_count u32 | 8 near_zero u64
+    uint32_t *st() const { return small.as<uint32_t>(); }
+    uint32_t *halo_count() const { return small.as<uint32_t>() + 1; }
+    unsigned long long *near() const { return reinterpret_cast<unsigned long long *>(small.as<uint8_t>() + 8); }
+};
+
+}  // namespace
+
+struct vx_ctx {
+    std::vector<Dev> devs;
+    std::mutex mu;
+};
+
+namespace {
+
+int check_params(const vx_noise_params *in, vx_noise_params *out)
+{
+    if (in) *out = *in;
+    else vx_default_noise_params(out);
+    if (out->octaves < 1 || out->octaves > VX_MAX_OCTAVES)
+        return fail(VX_ERR_BAD_ARG, "octaves must be in 1..%d (got %d)", VX_MAX_OCTAVES, out->octaves);
+    return VX_OK;
+}
+
+uint32_t table_size_for(size_t n)
+{
+    uint32_t t = 64;
+    while ((size_t)t < 2 * n + 2) t <<= 1;
+    return t;
+}
+
+// ---- device-side pipelines (everything async on stream s) -----------------
+
+// resolve neighbours of chunks [lo, hi) of the list into d.nbr
+int dev_resolve(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_all, uint32_t lo, uint32_t hi,
+                const uint8_t *d_mask_all, bool allow_halo)
+{
+    const uint32_t n = hi - lo;
+    CK(d.nbr.ensure((size_t)n * 16));
+    const uint32_t ts = table_size_for(n_all);
+    CK(d.table.ensure((size_t)ts * 4));
+    if (allow_halo) {
+        CK(d.halo_items.ensure((size_t)n * 4 * sizeof(vx_halo_item)));
+        CK(d.halo.ensure((size_t)n * 4 * 32 * 4));
+    }
+    vx_resolve_args r{};
+    r.coords = d_coords_all;
+    r.nbr_mask = d_mask_all;
+    r.n = n_all;
+    r.lo = lo;
+    r.hi = hi;
+    r.table = d.table.as<int32_t>();
+    r.table_size = ts;
+    r.nbr = d.nbr.as<int32_t>();
+    r.halo_items = allow_halo ? d.halo_items.as<vx_halo_item>() : nullptr;
+    r.halo_count = d.halo_count();
+    CK(vx_launch_resolve(r, s, &d.launches));
+    return VX_OK;
+}
+
+// noise fill of chunks [lo, hi) + their halo slabs, then count + scan
+int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_all, uint32_t lo, uint32_t hi,
+                  const vx_noise_params &p, const uint8_t *d_mask_all, uint32_t *d_counts, uint64_t *d_offsets,
+                  uint8_t *d_blocks)
+{
+    const uint32_t n = hi - lo;
+    if (n == 0) return VX_OK;
+    CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
+    const bool may_halo = d_mask_all != nullptr || lo != 0 || hi != n_all;
+    RET(dev_resolve(d, s, d_coords_all, n_all, lo, hi, d_mask_all, may_halo));
+
+    vx_fill_args f{};
+    f.coords = d_coords_all + 3 * (size_t)lo;
+    f.max_units = n * 32u;
+    f.p = p;
+    f.occ = d.occ.as<uint32_t>();
+    f.blocks = d_blocks;
+    CK(vx_launch_fill(f, false, s, &d.launches));
+    if (may_halo) {
+        vx_fill_args h{};
+        h.halo_items = d.halo_items.as<vx_halo_item>();
+        h.halo_count = d.halo_count();
+        h.max_units = n * 4u;
+        h.p = p;
+        h.occ = d.halo.as<uint32_t>();
+        CK(vx_launch_fill(h, true, s, &d.launches));
+    }
+    vx_mesh_args m{};
+    m.occ = d.occ.as<uint32_t>();
+    m.typ = nullptr;
+    m.halo = d.halo.as<uint32_t>();
+    m.coords = d_coords_all + 3 * (size_t)lo;
+    m.nbr = d.nbr.as<int32_t>();
+    m.counts = d_counts;
+    m.offsets = d_offsets;
+    m.n = n;
+    CK(vx_launch_mesh_count(m, s, &d.launches));
+    CK(vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    return VX_OK;
+}
+
+vx_mesh_args emit_args(const Dev &d, const int32_t *d_coords, const uint32_t *typ, const uint8_t *mesh_mask,
+                       uint32_t *d_counts, uint64_t *d_offsets, uint32_t n)
+{
+    vx_mesh_args m{};
+    m.occ = d.occ.as<uint32_t>();
+    m.typ = typ;
+    m.halo = d.halo.as<uint32_t>();
+    m.coords = d_coords;
+    m.nbr = d.nbr.as<int32_t>();
+    m.mesh_mask = mesh_mask;
+    m.counts = d_counts;
+    m.offsets = d_offsets;
+    m.n = n;
+    return m;
+}
+
+// Stream the instances of chunks [0, n) (device-local numbering, host copy of
+// the local offsets in h_off) to host memory through the two arenas.
+int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t n, vx_instance *h_out)
+{
+    CK(d.inst[0].ensure(kArenaBytes));
+    if (h_off[n] > kArenaQuads) CK(d.inst[1].ensure(kArenaBytes));
+    uint32_t a = 0;
+    int k = 0;
+    while (a < n) {
+        uint32_t b = a + 1;     // at least one chunk (<= 98304 quads always fits)
+        while (b < n && h_off[b + 1] - h_off[a] <= kArenaQuads) ++b;
+        const uint64_t q = h_off[b] - h_off[a];
+        if (q > 0) {
+            const int buf = k & 1;
+            CK(cudaStreamWaitEvent(d.stream, d.d2h_done[buf], 0));      // arena free again
+            m.out = d.inst[buf].as<vx_instance>();
+            m.capacity = kArenaQuads;
+            m.m0 = a;
+            m.quad_base = h_off[a];
+            m.status = d.st();
+            CK(vx_launch_mesh_emit(m, b - a, d.stream, &d.launches));
+            CK(cudaEventRecord(d.emit_done[buf], d.stream));
+            CK(cudaStreamWaitEvent(d.copy, d.emit_done[buf], 0));
+            CK(cudaMemcpyAsync(h_out + h_off[a], d.inst[buf].p, q * sizeof(vx_instance), cudaMemcpyDeviceToHost,
+                               d.copy));
+            CK(cudaEventRecord(d.d2h_done[buf], d.copy));
+            ++k;
+        }
+        a = b;
+    }
+    return VX_OK;
+}
+
+int sync_dev(Dev &d)
+{
+    CK(cudaSetDevice(d.id));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaStreamSynchronize(d.copy));
+    return VX_OK;
+}
+
+void split_range(size_t n, size_t nd, size_t d, size_t align, uint32_t *lo, uint32_t *hi)
+{
+    size_t per = (n + nd - 1) / nd;
+    per = (per + align - 1) / align * align;
+    size_t l = std::min(n, per * d), h = std::min(n, per * (d + 1));
+    *lo = (uint32_t)l;
+    *hi = (uint32_t)h;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int vx_version(void) { return VX_VERSION; }
+
+const char *vx_last_error(void) { return g_err.c_str(); }
+
+int vx_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VX_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+void vx_default_noise_params(vx_noise_params *p)
+{
+    // perlin_noise.rs:14-18
+    p->seed = 1;
+    p->freq = 0.09f;
+    p->gain = 2.5f;
+    p->lacunarity = 0.5f;
+    p->octaves = 3;
+}
+
+int vx_create(const int *devices, int n_devices, vx_ctx **out)
+{
+    if (!out) return fail(VX_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    const int avail = vx_device_count();
+    if (avail <= 0) return fail(VX_ERR_NO_DEVICE, "no CUDA device available (libvoxb200 has no CPU fallback)");
+    std::vector<int> ids;
+    if (devices) {
+        if (n_devices <= 0) return fail(VX_ERR_BAD_ARG, "n_devices must be > 0 when devices is given");
+        ids.assign(devices, devices + n_devices);
+    } else {
+        const int n = n_devices <= 0 ? avail : n_devices;
+        for (int i = 0; i < n; ++i) ids.push_back(i);
+    }
+    for (int id : ids)
+        if (id < 0 || id >= avail) return fail(VX_ERR_BAD_ARG, "device %d out of range (have %d)", id, avail);
+    vx_ctx *ctx = new vx_ctx();
+    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        Dev &d = ctx->devs[i];
+        d.id = ids[i];
+        cudaError_t e = cudaSetDevice(d.id);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaEventCreateWithFlags(&d.emit_done[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.d2h_done[b], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = d.small.ensure(64);
+        if (e == cudaSuccess) e = cudaMemset(d.small.p, 0, 64);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_small, 64, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            int r = cuda_fail(e, "context setup", __LINE__);
+            vx_destroy(ctx);
+            return r;
+        }
+    }
+    *out = ctx;
+    return VX_OK;
+}
+
+void vx_destroy(vx_ctx *ctx)
+{
+    if (!ctx) return;
+    for (Dev &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        for (DevBuf *b : {&d.coords, &d.mask8, &d.occ, &d.typ, &d.halo, &d.halo_items, &d.table, &d.nbr, &d.nbr_in,
+                          &d.counts, &d.offsets, &d.small, &d.blocks, &d.noise, &d.inst[0], &d.inst[1], &d.planes,
+                          &d.vis, &d.bits, &d.mesh_mask})
+            b->release();
+        if (d.h_small) cudaFreeHost(d.h_small);
+        for (int b = 0; b < 2; ++b) {
+            if (d.emit_done[b]) cudaEventDestroy(d.emit_done[b]);
+            if (d.d2h_done[b]) cudaEventDestroy(d.d2h_done[b]);
+        }
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.copy) cudaStreamDestroy(d.copy);
+    }
+    delete ctx;
+}
+
+int vx_num_devices(const vx_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+uint64_t vx_launch_count(const vx_ctx *ctx)
+{
+    uint64_t t = 0;
+    if (ctx)
+        for (const Dev &d : ctx->devs) t += d.launches;
+    return t;
+}
+
+int vx_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return fail(VX_ERR_BAD_ARG, "out is NULL");
+    if (vx_device_count() <= 0) return VX_ERR_NO_DEVICE;
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return VX_OK;
+}
+
+int vx_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return VX_OK;
+}
+
+int vx_sync(vx_ctx *ctx)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (Dev &d : ctx->devs) RET(sync_dev(d));
+    return VX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fill
+// ---------------------------------------------------------------------------
+int vx_fill_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                   uint8_t *blocks_out, float *noise_out, uint32_t *occupancy_out, uint64_t *near_zero_out,
+                   void *stream)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (n == 0) return VX_OK;
+    if (!coords) return fail(VX_ERR_BAD_ARG, "coords is NULL");
+    if (n > (size_t)0x7ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    vx_noise_params p;
+    RET(check_params(params, &p));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
+    uint32_t *occ = occupancy_out;
+    if (!occ) {
+        CK(d.occ.ensure(n * VX_ROWS * 4));
+        occ = d.occ.as<uint32_t>();
+    }
+    vx_fill_args f{};
+    f.coords = coords;
+    f.max_units = (uint32_t)n * 32u;
+    f.p = p;
+    f.occ = occ;
+    f.blocks = blocks_out;
+    f.noise = noise_out;
+    f.near_zero = reinterpret_cast<unsigned long long *>(near_zero_out);
+    if (near_zero_out) CK(cudaMemsetAsync(near_zero_out, 0, 8, s));
+    CK(vx_launch_fill(f, false, s, &d.launches));
+    return VX_OK;
+}
+
+int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params, uint8_t *blocks_out,
+            float *noise_out, uint32_t *occupancy_out, uint64_t *near_zero_out)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (near_zero_out) *near_zero_out = 0;
+    if (n == 0) return VX_OK;
+    if (!coords) return fail(VX_ERR_BAD_ARG, "coords is NULL");
+    if (n > (size_t)0x7ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    vx_noise_params p;
+    RET(check_params(params, &p));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t nd = ctx->devs.size();
+    const size_t per_chunk = VX_ROWS * 4 + (blocks_out ? VX_VOXELS : 0) + (noise_out ? VX_VOXELS * 4 : 0);
+    const size_t slice = std::max<size_t>(1, kSliceBytes / per_chunk);
+    for (size_t di = 0; di < nd; ++di) {
+        Dev &d = ctx->devs[di];
+        uint32_t lo, hi;
+        split_range(n, nd, di, 1, &lo, &hi);
+        if (hi <= lo) continue;
+        CK(cudaSetDevice(d.id));
+        const size_t nn = hi - lo, sl = std::min(slice, nn);
+        CK(d.coords.ensure(nn * 12));
+        CK(cudaMemcpyAsync(d.coords.p, coords + 3 * (size_t)lo, nn * 12, cudaMemcpyHostToDevice, d.stream));
+        CK(d.occ.ensure(sl * VX_ROWS * 4));
+        if (blocks_out) CK(d.blocks.ensure(sl * VX_VOXELS));
+        if (noise_out) CK(d.noise.ensure(sl * VX_VOXELS * 4));
+        if (near_zero_out) CK(cudaMemsetAsync(d.near(), 0, 8, d.stream));
+        for (size_t a = 0; a < nn; a += sl) {
+            const size_t c = std::min(sl, nn - a);
+            vx_fill_args f{};
+            f.coords = d.coords.as<int32_t>() + 3 * a;
+            f.max_units = (uint32_t)c * 32u;
+            f.p = p;
+            f.occ = d.occ.as<uint32_t>();
+            f.blocks = blocks_out ? d.blocks.as<uint8_t>() : nullptr;
+            f.noise = noise_out ? d.noise.as<float>() : nullptr;
+            f.near_zero = near_zero_out ? d.near() : nullptr;
+            CK(vx_launch_fill(f, false, d.stream, &d.launches));
+            const size_t g = lo + a;
+            if (blocks_out)
+                CK(cudaMemcpyAsync(blocks_out + g * VX_VOXELS, d.blocks.p, c * VX_VOXELS, cudaMemcpyDeviceToHost,
+                                   d.stream));
+            if (noise_out)
+                CK(cudaMemcpyAsync(noise_out + g * VX_VOXELS, d.noise.p, c * VX_VOXELS * 4, cudaMemcpyDeviceToHost,
+                                   d.stream));
+            if (occupancy_out)
+                CK(cudaMemcpyAsync(occupancy_out + g * VX_ROWS, d.occ.p, c * VX_ROWS * 4, cudaMemcpyDeviceToHost,
+                                   d.stream));
+        }
+        if (near_zero_out) CK(cudaMemcpyAsync(d.h_small + 2, d.near(), 8, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (Dev &d : ctx->devs) {
+        RET(sync_dev(d));
+        if (near_zero_out) {
+            uint64_t v;
+            memcpy(&v, d.h_small + 2, 8);
+            *near_zero_out += v;
+            memset(d.h_small + 2, 0, 8);
+        }
+    }
+    return VX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// mesh of caller-provided blocks (first GPU of the context)
+// ---------------------------------------------------------------------------
+static int mesh_prepare(Dev &d, cudaStream_t s, const int32_t *d_coords, uint32_t n, const uint8_t *d_blocks,
+                        const int32_t *d_nbr_idx, uint32_t *d_counts, uint64_t *d_offsets,
+                        const uint8_t *d_mesh_mask, uint32_t *d_status)
+{
+    CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
+    CK(d.typ.ensure((size_t)n * VX_ROWS * 4));
+    CK(vx_launch_pack(d_blocks, n, d.occ.as<uint32_t>(), d.typ.as<uint32_t>(), d_status, s, &d.launches));
+    if (d_nbr_idx) {
+        CK(d.nbr.ensure((size_t)n * 16));
+        CK(vx_launch_remap_nbr(d_nbr_idx, d.nbr.as<int32_t>(), n, s, &d.launches));
+    } else {
+        RET(dev_resolve(d, s, d_coords, n, 0, n, nullptr, false));
+    }
+    vx_mesh_args m = emit_args(d, d_coords, d.typ.as<uint32_t>(), d_mesh_mask, d_counts, d_offsets, n);
+    CK(vx_launch_mesh_count(m, s, &d.launches));
+    CK(vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    return VX_OK;
+}
+
+int vx_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
+                   const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                   size_t capacity, uint32_t *status, void *stream)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (!offsets || (n && (!coords || !blocks || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
+    if (status) CK(cudaMemsetAsync(status, 0, 4, s));
+    if (n == 0) {
+        CK(cudaMemsetAsync(offsets, 0, 8, s));
+        return VX_OK;
+    }
+    RET(mesh_prepare(d, s, coords, (uint32_t)n, blocks, nbr_idx, counts, offsets, mesh_mask, status));
+    if (instances) {
+        vx_mesh_args m = emit_args(d, coords, d.typ.as<uint32_t>(), mesh_mask, counts, offsets, (uint32_t)n);
+        m.out = instances;
+        m.capacity = capacity;
+        m.status = status;
+        CK(vx_launch_mesh_emit(m, (uint32_t)n, s, &d.launches));
+    }
+    return VX_OK;
+}
+
+int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
+            const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances, size_t capacity,
+            uint64_t *total_out)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (total_out) *total_out = 0;
+    if (!offsets || (n && (!coords || !blocks || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    offsets[0] = 0;
+    if (n == 0) return VX_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = d.stream;
+    const uint32_t nn = (uint32_t)n;
+    CK(d.coords.ensure(n * 12));
+    CK(d.blocks.ensure(n * VX_VOXELS));
+    CK(d.counts.ensure(n * 4));
+    CK(d.offsets.ensure((n + 1) * 8));
+    CK(cudaMemcpyAsync(d.coords.p, coords, n * 12, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.blocks.p, blocks, n * VX_VOXELS, cudaMemcpyHostToDevice, s));
+    const int32_t *d_nbr_idx = nullptr;
+    if (nbr_idx) {
+        for (size_t i = 0; i < n * 4; ++i)
+            if (nbr_idx[i] >= (int64_t)n) return fail(VX_ERR_BAD_ARG, "nbr_idx[%zu] = %d out of range", i, nbr_idx[i]);
+        CK(d.nbr_in.ensure(n * 16));
+        CK(cudaMemcpyAsync(d.nbr_in.p, nbr_idx, n * 16, cudaMemcpyHostToDevice, s));
+        d_nbr_idx = d.nbr_in.as<int32_t>();
+    }
+    const uint8_t *d_mm = nullptr;
+    if (mesh_mask) {
+        CK(d.mesh_mask.ensure(n));
+        CK(cudaMemcpyAsync(d.mesh_mask.p, mesh_mask, n, cudaMemcpyHostToDevice, s));
+        d_mm = d.mesh_mask.as<uint8_t>();
+    }
+    CK(cudaMemsetAsync(d.st(), 0, 4, s));
+    RET(mesh_prepare(d, s, d.coords.as<int32_t>(), nn, d.blocks.as<uint8_t>(), d_nbr_idx, d.counts.as<uint32_t>(),
+                     d.offsets.as<uint64_t>(), d_mm, d.st()));
+    CK(cudaMemcpyAsync(counts, d.counts.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(offsets, d.offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(d.h_small, d.st(), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (d.h_small[0] & VX_ST_BAD_BLOCK)
+        return fail(VX_ERR_BAD_BLOCK, "blocks contain an id outside {0 GRASS, 1 DIRT, 2 AIR} (cube.rs:16-21)");
+    const uint64_t total = offsets[n];
+    if (total_out) *total_out = total;
+    if (!instances) return VX_OK;
+    if (total > capacity)
+        return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
+    vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), d.typ.as<uint32_t>(), d_mm, d.counts.as<uint32_t>(),
+                               d.offsets.as<uint64_t>(), nn);
+    RET(dev_stream_instances(d, m, offsets, nn, instances));
+    RET(sync_dev(d));
+    return VX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused generate + mesh
+// ---------------------------------------------------------------------------
+int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                       const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                       size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (!offsets || (n && (!coords || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    vx_noise_params p;
+    RET(check_params(params, &p));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
+    if (status) CK(cudaMemsetAsync(status, 0, 4, s));
+    if (n == 0) {
+        CK(cudaMemsetAsync(offsets, 0, 8, s));
+        return VX_OK;
+    }
+    const uint32_t nn = (uint32_t)n;
+    RET(dev_gen_count(d, s, coords, nn, 0, nn, p, nbr_mask, counts, offsets, blocks_out));
+    if (instances) {
+        vx_mesh_args m = emit_args(d, coords, nullptr, nullptr, counts, offsets, nn);
+        m.out = instances;
+        m.capacity = capacity;
+        m.status = status;
+        CK(vx_launch_mesh_emit(m, nn, s, &d.launches));
+    }
+    return VX_OK;
+}
+
+int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                size_t capacity, uint64_t *total_out, uint8_t *blocks_out)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (total_out) *total_out = 0;
+    if (!offsets || (n && (!coords || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
+    offsets[0] = 0;
+    if (n == 0) return VX_OK;
+    vx_noise_params p;
+    RET(check_params(params, &p));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t nd = ctx->devs.size();
+    const uint32_t nn = (uint32_t)n;
+    std::vector<uint32_t> lo(nd), hi(nd);
+    std::vector<std::vector<uint64_t>> loc(nd);     // device-local offsets
+
+    for (size_t di = 0; di < nd; ++di) {
+        Dev &d = ctx->devs[di];
+        split_range(n, nd, di, 1, &lo[di], &hi[di]);
+        const uint32_t c = hi[di] - lo[di];
+        if (c == 0) continue;
+        CK(cudaSetDevice(d.id));
+        CK(d.coords.ensure(n * 12));
+        CK(cudaMemcpyAsync(d.coords.p, coords, n * 12, cudaMemcpyHostToDevice, d.stream));
+        const uint8_t *d_mask = nullptr;
+        if (nbr_mask) {
+            CK(d.mask8.ensure(n));
+            CK(cudaMemcpyAsync(d.mask8.p, nbr_mask, n, cudaMemcpyHostToDevice, d.stream));
+            d_mask = d.mask8.as<uint8_t>();
+        }
+        CK(d.counts.ensure((size_t)c * 4));
+        CK(d.offsets.ensure(((size_t)c + 1) * 8));
+        uint8_t *d_blocks = nullptr;
+        if (blocks_out) {
+            CK(d.blocks.ensure((size_t)c * VX_VOXELS));
+            d_blocks = d.blocks.as<uint8_t>();
+        }
+        CK(cudaMemsetAsync(d.st(), 0, 4, d.stream));
+        RET(dev_gen_count(d, d.stream, d.coords.as<int32_t>(), nn, lo[di], hi[di], p, d_mask,
+                          d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), d_blocks));
+        loc[di].resize((size_t)c + 1);
+        CK(cudaMemcpyAsync(counts + lo[di], d.counts.p, (size_t)c * 4, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpyAsync(loc[di].data(), d.offsets.p, ((size_t)c + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+        if (blocks_out)
+            CK(cudaMemcpyAsync(blocks_out + (size_t)lo[di] * VX_VOXELS, d.blocks.p, (size_t)c * VX_VOXELS,
+                               cudaMemcpyDeviceToHost, d.stream));
+    }
+    uint64_t total = 0;
+    std::vector<uint64_t> base(nd, 0);
+    for (size_t di = 0; di < nd; ++di) {
+        if (hi[di] == lo[di]) continue;
+        Dev &d = ctx->devs[di];
+        CK(cudaSetDevice(d.id));
+        CK(cudaStreamSynchronize(d.stream));
+        base[di] = total;
+        const uint32_t c = hi[di] - lo[di];
+        for (uint32_t i = 0; i < c; ++i) offsets[lo[di] + i] = total + loc[di][i];
+        total += loc[di][c];
+    }
+    offsets[n] = total;
+    if (total_out) *total_out = total;
+    if (!instances) return VX_OK;
+    if (total > capacity)
+        return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
+    for (size_t di = 0; di < nd; ++di) {
+        const uint32_t c = hi[di] - lo[di];
+        if (c == 0) continue;
+        Dev &d = ctx->devs[di];
+        CK(cudaSetDevice(d.id));
+        vx_mesh_args m = emit_args(d, d.coords.as<int32_t>() + 3 * (size_t)lo[di], nullptr, nullptr,
+                                   d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), c);
+        RET(dev_stream_instances(d, m, loc[di].data(), c, instances + base[di]));
+    }
+    for (Dev &d : ctx->devs) RET(sync_dev(d));
+    return VX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// frustum
+// ---------------------------------------------------------------------------
+int vx_planes_from_matrix(const float m[16], float planes[24])
+{
+    if (!m || !planes) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    // frustum_culling.rs:47-85: data[c][r] = m[c*4 + r]; planes = row3 +- row{0,1,2};
+    // stored order near, far, left, right, top, bottom (:84); not normalised.
+    // (24 scalar adds, once per frame -- host-side bookkeeping, not the data path.)
+    for (int c = 0; c < 4; ++c) {
+        const float r0 = m[c * 4 + 0], r1 = m[c * 4 + 1], r2 = m[c * 4 + 2], r3 = m[c * 4 + 3];
+        planes[0 * 4 + c] = r3 + r2;   // near   :75-78
+        planes[1 * 4 + c] = r3 - r2;   // far    :80-83
+        planes[2 * 4 + c] = r3 + r0;   // left   :55-58
+        planes[3 * 4 + c] = r3 - r0;   // right  :60-63
+        planes[4 * 4 + c] = r3 - r1;   // top    :65-68
+        planes[5 * 4 + c] = r3 + r1;   // bottom :70-73
+    }
+    return VX_OK;
+}
+
+int vx_frustum_cull_device(vx_ctx *ctx, const float *planes, size_t n_frames, const int32_t *coords, size_t n,
+                           uint8_t *visible, uint32_t *bits, void *stream)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (n == 0 || n_frames == 0) return VX_OK;
+    if (!planes || !coords || (!visible && !bits)) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > 0x7fffffffu || n_frames > 65535u * 64u) return fail(VX_ERR_BAD_ARG, "n or n_frames too large");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
+    CK(vx_launch_frustum(planes, (uint32_t)n_frames, coords, (uint32_t)n, visible, bits, s, &d.launches));
+    return VX_OK;
+}
+
+static int frustum_host(vx_ctx *ctx, const float *planes, size_t n_frames, const int32_t *coords, size_t n,
+                        uint8_t *visible, uint32_t *bits)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (n == 0 || n_frames == 0) return VX_OK;
+    if (!planes || !coords || (!visible && !bits)) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (n > 0x7fffffffu) return fail(VX_ERR_BAD_ARG, "n too large");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t nd = ctx->devs.size();
+    const size_t n_words = (n + 31) / 32;
+    for (size_t di = 0; di < nd; ++di) {
+        Dev &d = ctx->devs[di];
+        uint32_t lo, hi;
+        split_range(n, nd, di, 32, &lo, &hi);       // shards start on a bit-word boundary
+        if (hi <= lo) continue;
+        const size_t c = hi - lo, cw = (c + 31) / 32;
+        CK(cudaSetDevice(d.id));
+        CK(d.coords.ensure(c * 12));
+        CK(cudaMemcpyAsync(d.coords.p, coords + 3 * (size_t)lo, c * 12, cudaMemcpyHostToDevice, d.stream));
+        const size_t per_frame = visible ? c : cw * 4;
+        const size_t fs = std::min(n_frames, std::max<size_t>(1, kSliceBytes / per_frame));
+        CK(d.planes.ensure(n_frames * 96));
+        CK(cudaMemcpyAsync(d.planes.p, planes, n_frames * 96, cudaMemcpyHostToDevice, d.stream));
+        if (visible) CK(d.vis.ensure(fs * c));
+        else CK(d.bits.ensure(fs * cw * 4));
+        for (size_t f = 0; f < n_frames; f += fs) {
+            const size_t nf = std::min(fs, n_frames - f);
+            CK(vx_launch_frustum(d.planes.as<float>() + f * 24, (uint32_t)nf, d.coords.as<int32_t>(), (uint32_t)c,
+                                 visible ? d.vis.as<uint8_t>() : nullptr, visible ? nullptr : d.bits.as<uint32_t>(),
+                                 d.stream, &d.launches));
+            if (visible)
+                CK(cudaMemcpy2DAsync(visible + f * n + lo, n, d.vis.p, c, c, nf, cudaMemcpyDeviceToHost, d.stream));
+            else
+                CK(cudaMemcpy2DAsync(bits + f * n_words + lo / 32, n_words * 4, d.bits.p, cw * 4, cw * 4, nf,
+                                     cudaMemcpyDeviceToHost, d.stream));
+        }
+    }
+    for (Dev &d : ctx->devs) RET(sync_dev(d));
+    return VX_OK;
+}
+
+int vx_frustum_cull(vx_ctx *ctx, const float *planes, size_t n_frames, const int32_t *coords, size_t n,
+                    uint8_t *visible)
+{
+    if (!visible && n && n_frames) return fail(VX_ERR_BAD_ARG, "visible is NULL");
+    return frustum_host(ctx, planes, n_frames, coords, n, visible, nullptr);
+}
+
+int vx_frustum_cull_bits(vx_ctx *ctx, const float *planes, size_t n_frames, const int32_t *coords, size_t n,
+                         uint32_t *bits)
+{
+    if (!bits && n && n_frames) return fail(VX_ERR_BAD_ARG, "bits is NULL");
+    return frustum_host(ctx, planes, n_frames, coords, n, nullptr, bits);
+}
+
+// ---------------------------------------------------------------------------
+int vx_measure_peak(vx_ctx *ctx, int kind, double *tera_ops)
+{
+    if (!ctx || !tera_ops) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(VX_ERR_BAD_ARG, "kind must be 0, 1 or 2");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    CK(cudaSetDevice(d.id));
+    CK(vx_run_peak(kind, d.n_sm, tera_ops, d.stream, &d.launches));
+    return VX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// kernels_fill.cu -- batched terrain fill: noise -> threshold -> occupancy
+// bitmasks (+ optional block ids / noise field).  Replaces
+// perlin_noise.rs:5-22 + chunk.rs:27-46 for thousands of chunks per launch.
+//
+// Work unit = one warp = one 32x32 voxel slab of one chunk:
+//   full-chunk mode: unit (chunk, z); lane = x; the warp walks y = 0..31.
+//     One __ballot_sync per y gives the occupancy word of row (y, z).
+//   halo mode: unit = one border slab of a chunk that is NOT in the batch
+//     (kind 0/1: x fixed, lane = z; kind 2/3: z fixed, lane = x).
+// x and z (simdnoise x and y, perlin_noise.rs:7-12) are invariant along the
+// walk, so their per-octave products and x+y sums are hoisted.
+// FP32 ALU + INT32 bound; no tensor cores (nothing here is a contraction).
+#include "vx_common.cuh"
+#include "vx_noise.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+template <int OCT, bool HALO, bool WANT_NOISE, bool WANT_BLOCKS, bool WANT_CENSUS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+vx_fill_kernel(const vx_fill_args a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t unit = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    uint32_t limit = a.max_units;
+    if (HALO) limit = min(limit, *a.halo_count);
+    if (unit >= limit) return;
+
+    int32_t cx, cy, cz;
+    uint32_t item, fixed_axis_is_x = 0, fixed_val;
+    if (HALO) {
+        const vx_halo_item it = a.halo_items[unit];
+        cx = it.cx; cy = it.cy; cz = it.cz;
+        item = unit;
+        fixed_axis_is_x = (it.kind < 2);
+        fixed_val = (it.kind == 0 || it.kind == 2) ? 31u : 0u;
+    } else {
+        item = unit >> 5;
+        fixed_val = unit & 31u;                    // z
+        cx = a.coords[3 * item + 0];
+        cy = a.coords[3 * item + 1];
+        cz = a.coords[3 * item + 2];
+    }
+    // perlin_noise.rs:7-12: simdnoise (x, y, z) = engine (x, z, y); origins are
+    // (pos * 32) as f32 with a wrapping i32 product; lattice = origin + index.
+    const float ox = (float)(int32_t)((uint32_t)cx * 32u);
+    const float oy = (float)(int32_t)((uint32_t)cz * 32u);
+    const float oz = (float)(int32_t)((uint32_t)cy * 32u);
+    const uint32_t vx_ = fixed_axis_is_x ? fixed_val : lane;
+    const uint32_t vz_ = fixed_axis_is_x ? lane : fixed_val;
+    const float sx = __fadd_rn(ox, (float)vx_);
+    const float sy = __fadd_rn(oy, (float)vz_);
+
+    const int oct = (OCT > 0) ? OCT : a.p.octaves;
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const uint32_t seed = (uint32_t)a.p.seed;
+
+    constexpr int kHoist = (OCT > 0) ? OCT : 1;
+    float hx[kHoist], hy[kHoist], hxy[kHoist], hamp[kHoist];
+    hx[0] = __fmul_rn(sx, freq);
+    hy[0] = __fmul_rn(sy, freq);
+    hxy[0] = __fadd_rn(hx[0], hy[0]);
+    hamp[0] = 1.0f;
+#pragma unroll
+    for (int o = 1; o < kHoist; ++o) {
+        hx[o] = __fmul_rn(hx[o - 1], lac);
+        hy[o] = __fmul_rn(hy[o - 1], lac);
+        hxy[o] = __fadd_rn(hx[o], hy[o]);
+        hamp[o] = __fmul_rn(hamp[o - 1], gain);
+    }
+
+    uint32_t my_word = 0, near = 0;
+    float *noise_row = nullptr;
+    if (WANT_NOISE) noise_row = a.noise + (size_t)item * VX_VOXELS + fixed_val * 32u + lane;
+
+#pragma unroll 2
+    for (uint32_t y = 0; y < 32u; ++y) {
+        float z = __fmul_rn(__fadd_rn(oz, (float)y), freq);
+        float r = vxn_simplex3(hx[0], hy[0], z, hxy[0], seed);
+        if (OCT > 0) {
+#pragma unroll
+            for (int o = 1; o < kHoist; ++o) {
+                z = __fmul_rn(z, lac);
+                r = __fadd_rn(__fmul_rn(vxn_simplex3(hx[o], hy[o], z, hxy[o], seed), hamp[o]), r);
+            }
+        } else {
+            float x = hx[0], yy = hy[0], amp = 1.0f;
+            for (int o = 1; o < oct; ++o) {
+                x = __fmul_rn(x, lac);
+                yy = __fmul_rn(yy, lac);
+                z = __fmul_rn(z, lac);
+                amp = __fmul_rn(amp, gain);
+                r = __fadd_rn(__fmul_rn(vxn_simplex3(x, yy, z, __fadd_rn(x, yy), seed), amp), r);
+            }
+        }
+        // chunk.rs:38: noise < 0. -> GRASS, else AIR (+-0 and NaN are AIR)
+        const uint32_t word = __ballot_sync(VX_FULL, r < 0.0f);
+        if (lane == y) my_word = word;
+        if (WANT_NOISE) noise_row[(size_t)y * 1024u] = r;
+        if (WANT_CENSUS) near += (fabsf(r) <= 1e-6f) ? 1u : 0u;
+    }
+
+    if (HALO) {
+        a.occ[(size_t)item * 32u + lane] = my_word;          // word y: bit = lane axis
+        return;
+    }
+    a.occ[(size_t)item * VX_ROWS + lane * 32u + fixed_val] = my_word;   // row (y = lane, z)
+
+    if (WANT_BLOCKS) {
+        // 32 rows x 32 bytes of CubeType for this (chunk, z): 2 x 128-bit stores
+        // per lane; byte = AIR (2) where the occupancy bit is clear, GRASS (0) else.
+        uint8_t *base = a.blocks + (size_t)item * VX_VOXELS + fixed_val * 32u;
+#pragma unroll
+        for (uint32_t s = 0; s < 2u; ++s) {
+            const uint32_t c = s * 32u + lane;          // 16-byte piece index
+            const uint32_t y = c >> 1, half = c & 1u;
+            const uint32_t w = __shfl_sync(VX_FULL, my_word, y);
+            const uint32_t air16 = ~(w >> (16u * half)) & 0xffffu;
+            uint4 v;
+            v.x = (((air16 >> 0) & 15u) * 0x00204081u & 0x01010101u) << 1;
+            v.y = (((air16 >> 4) & 15u) * 0x00204081u & 0x01010101u) << 1;
+            v.z = (((air16 >> 8) & 15u) * 0x00204081u & 0x01010101u) << 1;
+            v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
+            *reinterpret_cast<uint4 *>(base + (size_t)y * 1024u + half * 16u) = v;
+        }
+    }
+    if (WANT_CENSUS) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) near += __shfl_xor_sync(VX_FULL, near, d);
+        if (lane == 0 && near) atomicAdd(a.near_zero, (unsigned long long)near);
+    }
+}
+
+template <int OCT, bool HALO>
+cudaError_t launch_oct(const vx_fill_args &a, cudaStream_t s)
+{
+    const uint32_t grid = (a.max_units + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid == 0) return cudaSuccess;
+    const dim3 block(kWarpsPerCta * 32);
+    if (HALO) {
+        vx_fill_kernel<OCT, true, false, false, false><<<grid, block, 0, s>>>(a);
+    } else {
+        const bool n = a.noise != nullptr, b = a.blocks != nullptr, c = a.near_zero != nullptr;
+        if (!n && !c) {
+            if (b) vx_fill_kernel<OCT, false, false, true, false><<<grid, block, 0, s>>>(a);
+            else vx_fill_kernel<OCT, false, false, false, false><<<grid, block, 0, s>>>(a);
+        } else {
+            // instrumented variant: noise and/or census (and blocks if asked)
+            if (n && c) {
+                if (b) vx_fill_kernel<OCT, false, true, true, true><<<grid, block, 0, s>>>(a);
+                else vx_fill_kernel<OCT, false, true, false, true><<<grid, block, 0, s>>>(a);
+            } else if (n) {
+                if (b) vx_fill_kernel<OCT, false, true, true, false><<<grid, block, 0, s>>>(a);
+                else vx_fill_kernel<OCT, false, true, false, false><<<grid, block, 0, s>>>(a);
+            } else {
+                if (b) vx_fill_kernel<OCT, false, false, true, true><<<grid, block, 0, s>>>(a);
+                else vx_fill_kernel<OCT, false, false, false, true><<<grid, block, 0, s>>>(a);
+            }
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, uint64_t *launches)
+{
+    if (a.max_units == 0) return cudaSuccess;
+    if (launches) ++*launches;
+    // octaves = 3 (perlin_noise.rs:18) gets the fully hoisted instantiation;
+    // anything else runs the generic loop.
+    if (a.p.octaves == 3)
+        return halo_mode ? launch_oct<3, true>(a, s) : launch_oct<3, false>(a, s);
+    return halo_mode ? launch_oct<0, true>(a, s) : launch_oct<0, false>(a, s);
+}

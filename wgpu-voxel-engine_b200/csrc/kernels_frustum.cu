@@ -1,0 +1,88 @@
+// kernels_frustum.cu -- Frustum::contains (frustum_culling.rs:16-40) for
+// n chunk AABBs x F plane sets per launch.
+//
+// One lane owns one chunk and keeps its six AABB coordinates in registers; a
+// CTA covers 256 chunks x up to kFramesPerCta frames whose planes are staged
+// in shared memory (warp-uniform broadcast reads).  The distance is evaluated
+// exactly as the reference does, ((a*x + b*y) + c*z) + d with every product
+// and sum rounded separately (frustum_culling.rs:29-32), and a corner is
+// rejected iff dist < 0 (NaN passes, :33-35).  The result is "any corner
+// inside all six planes" (:37) -- a pure function, so planes may be skipped
+// once no lane of the warp has a live corner.
+#include "vx_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kFramesPerCta = 64;
+
+template <bool WANT_BYTES, bool WANT_BITS>
+__global__ void __launch_bounds__(kThreads)
+vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
+                  const int32_t *__restrict__ coords, uint32_t n,
+                  uint8_t *__restrict__ visible, uint32_t *__restrict__ bits, uint32_t n_words)
+{
+    __shared__ float4 s_pl[kFramesPerCta * 6];
+    const uint32_t f0 = blockIdx.y * kFramesPerCta;
+    const uint32_t nf = min((uint32_t)kFramesPerCta, n_frames - f0);
+    for (uint32_t i = threadIdx.x; i < nf * 6; i += kThreads)
+        s_pl[i] = __ldg(reinterpret_cast<const float4 *>(planes) + (size_t)f0 * 6 + i);
+    __syncthreads();
+
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const bool live = i < n;
+    // coordinate.rs:53-58: (chunk * 32) as f32 (wrapping i32 product);
+    // frustum_culling.rs:19-26: the far corners are p + 32.
+    float x0 = 0.f, y0 = 0.f, z0 = 0.f;
+    if (live) {
+        x0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 0) * 32u);
+        y0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 1) * 32u);
+        z0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 2) * 32u);
+    }
+    const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
+
+    for (uint32_t f = 0; f < nf; ++f) {
+        bool in0 = live, in1 = live, in2 = live, in3 = live, in4 = live, in5 = live, in6 = live, in7 = live;
+#pragma unroll 1
+        for (uint32_t p = 0; p < 6; ++p) {
+            const float4 pl = s_pl[f * 6 + p];
+            const float ax0 = __fmul_rn(pl.x, x0), ax1 = __fmul_rn(pl.x, x1);
+            const float by0 = __fmul_rn(pl.y, y0), by1 = __fmul_rn(pl.y, y1);
+            const float cz0 = __fmul_rn(pl.z, z0), cz1 = __fmul_rn(pl.z, z1);
+            const float s00 = __fadd_rn(ax0, by0), s10 = __fadd_rn(ax1, by0);
+            const float s01 = __fadd_rn(ax0, by1), s11 = __fadd_rn(ax1, by1);
+            in0 = in0 && !(__fadd_rn(__fadd_rn(s00, cz0), pl.w) < 0.0f);
+            in1 = in1 && !(__fadd_rn(__fadd_rn(s10, cz0), pl.w) < 0.0f);
+            in2 = in2 && !(__fadd_rn(__fadd_rn(s00, cz1), pl.w) < 0.0f);
+            in3 = in3 && !(__fadd_rn(__fadd_rn(s10, cz1), pl.w) < 0.0f);
+            in4 = in4 && !(__fadd_rn(__fadd_rn(s01, cz0), pl.w) < 0.0f);
+            in5 = in5 && !(__fadd_rn(__fadd_rn(s11, cz0), pl.w) < 0.0f);
+            in6 = in6 && !(__fadd_rn(__fadd_rn(s01, cz1), pl.w) < 0.0f);
+            in7 = in7 && !(__fadd_rn(__fadd_rn(s11, cz1), pl.w) < 0.0f);
+            const bool any = in0 || in1 || in2 || in3 || in4 || in5 || in6 || in7;
+            if (!__any_sync(VX_FULL, any)) break;
+        }
+        const bool vis = in0 || in1 || in2 || in3 || in4 || in5 || in6 || in7;
+        const uint32_t word = __ballot_sync(VX_FULL, vis);
+        if (WANT_BYTES && live) visible[(size_t)(f0 + f) * n + i] = vis ? 1 : 0;
+        if (WANT_BITS && (threadIdx.x & 31) == 0 && live) bits[(size_t)(f0 + f) * n_words + (i >> 5)] = word;
+    }
+}
+
+}  // namespace
+
+cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
+                              uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches)
+{
+    if (n == 0 || n_frames == 0) return cudaSuccess;
+    const dim3 grid((n + kThreads - 1) / kThreads, (n_frames + kFramesPerCta - 1) / kFramesPerCta);
+    const uint32_t n_words = (n + 31) / 32;
+    if (visible && bits)
+        vx_frustum_kernel<true, true><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);
+    else if (visible)
+        vx_frustum_kernel<true, false><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);
+    else
+        vx_frustum_kernel<false, true><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}

@@ -1,0 +1,85 @@
+// vx_noise.cuh -- simdnoise 3.1.6 `fbm_3d` over hashed `simplex_3d`, one lane
+// per voxel.  Follows the reference's call shape perlin_noise.rs:5-22 and the
+// crate's published algorithm.  Every f32 operation is a
+// separately rounded IEEE op (__fmul_rn/__fadd_rn are never contracted into
+// FMA), integer arithmetic wraps mod 2^32 and the hash shift is arithmetic,
+// so results are bit-identical to the scalar/AVX2 CPU evaluation.
+#pragma once
+#include <cstdint>
+
+#define VXN_F3 0x1.555556p-2f      /* (f32)(1/3) */
+#define VXN_G3 0x1.555556p-3f      /* (f32)(1/6) */
+#define VXN_G33 (-0.5f)            /* 3/6 - 1    */
+#define VXN_XP 1619u
+#define VXN_YP 31337u
+#define VXN_ZP 6971u
+
+__device__ __forceinline__ float vxn_grad(uint32_t h, float x, float y, float z)
+{
+    // h = ((i ^ seed) ^ j) ^ k  (xor order is irrelevant)
+    h = ((h * h) * 60493u) * h;
+    h = (uint32_t)(((int32_t)h) >> 13) ^ h;
+    // h13 = h & 13:  h13 < 8  <=> bit 3 clear;  h13 < 2 <=> bits 2,3 clear;
+    // h13 == 12 <=> bits 2,3 set (bit 0 is free in all three tests)
+    const float u = (h & 8u) ? y : x;
+    const float v = ((h & 12u) == 0u) ? y : (((~h) & 12u) == 0u ? x : z);
+    const float su = __uint_as_float(__float_as_uint(u) ^ (h << 31));
+    const float sv = __uint_as_float(__float_as_uint(v) ^ ((h << 30) & 0x80000000u));
+    return __fadd_rn(su, sv);
+}
+
+__device__ __forceinline__ float vxn_weight(float a, float b, float c)
+{
+    float t = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(a, a)), __fmul_rn(b, b)), __fmul_rn(c, c));
+    t = fmaxf(t, 0.0f);              // cmpge mask: negatives (and NaN) -> 0; one FMNMX
+    t = __fmul_rn(t, t);
+    return __fmul_rn(t, t);
+}
+
+// xy = x + y is passed in so callers can hoist it when x and y are loop
+// invariant; it must be exactly __fadd_rn(x, y).
+__device__ __forceinline__ float vxn_simplex3(float x, float y, float z, float xy, uint32_t seed)
+{
+    const float f = __fmul_rn(VXN_F3, __fadd_rn(xy, z));
+    const float xf = floorf(__fadd_rn(x, f));
+    const float yf = floorf(__fadd_rn(y, f));
+    const float zf = floorf(__fadd_rn(z, f));
+
+    // Lattice hashes.  Each axis only ever takes two values over the four
+    // simplex corners (base, base + PRIME), so both are formed once and the
+    // middle corners select between them; the seed is folded into the x term.
+    const uint32_t ib0 = (uint32_t)__float2int_rz(xf) * VXN_XP;
+    const uint32_t ia = ib0 ^ seed, ib = (ib0 + VXN_XP) ^ seed;
+    const uint32_t ja = (uint32_t)__float2int_rz(yf) * VXN_YP, jb = ja + VXN_YP;
+    const uint32_t ka = (uint32_t)__float2int_rz(zf) * VXN_ZP, kb = ka + VXN_ZP;
+
+    const float g = __fmul_rn(VXN_G3, __fadd_rn(__fadd_rn(xf, yf), zf));
+    const float x0 = __fsub_rn(x, __fsub_rn(xf, g));
+    const float y0 = __fsub_rn(y, __fsub_rn(yf, g));
+    const float z0 = __fsub_rn(z, __fsub_rn(zf, g));
+
+    const bool xy_ = x0 >= y0, yz_ = y0 >= z0, xz_ = x0 >= z0;
+    const bool i1 = xy_ && xz_, j1 = !xy_ && yz_, k1 = !xz_ && !yz_;
+    const bool i2 = xy_ || xz_, j2 = !xy_ || yz_, k2 = !(xz_ && yz_);
+
+    // (x0 + (m ? -1 : 0)) + C: the -1 sum is shared by corners 1 and 2.  The
+    // "+ 0" arm only differs from x0 for -0, which the following + C absorbs.
+    const float xm = __fadd_rn(x0, -1.0f), ym = __fadd_rn(y0, -1.0f), zm = __fadd_rn(z0, -1.0f);
+    const float x1 = __fadd_rn(i1 ? xm : x0, VXN_G3);
+    const float y1 = __fadd_rn(j1 ? ym : y0, VXN_G3);
+    const float z1 = __fadd_rn(k1 ? zm : z0, VXN_G3);
+    const float x2 = __fadd_rn(i2 ? xm : x0, VXN_F3);
+    const float y2 = __fadd_rn(j2 ? ym : y0, VXN_F3);
+    const float z2 = __fadd_rn(k2 ? zm : z0, VXN_F3);
+    const float x3 = __fadd_rn(x0, VXN_G33);
+    const float y3 = __fadd_rn(y0, VXN_G33);
+    const float z3 = __fadd_rn(z0, VXN_G33);
+
+    const float v0 = __fmul_rn(vxn_weight(x0, y0, z0), vxn_grad(ia ^ ja ^ ka, x0, y0, z0));
+    const float v1 = __fmul_rn(vxn_weight(x1, y1, z1),
+                               vxn_grad((i1 ? ib : ia) ^ (j1 ? jb : ja) ^ (k1 ? kb : ka), x1, y1, z1));
+    const float v2 = __fmul_rn(vxn_weight(x2, y2, z2),
+                               vxn_grad((i2 ? ib : ia) ^ (j2 ? jb : ja) ^ (k2 ? kb : ka), x2, y2, z2));
+    const float v3 = __fmul_rn(vxn_weight(x3, y3, z3), vxn_grad(ib ^ jb ^ kb, x3, y3, z3));
+    return __fadd_rn(__fadd_rn(__fadd_rn(v3, v2), v1), v0);
+}

@@ -176,6 +176,24 @@ int vx_sync(vx_ctx *ctx);
  * 2 = INT32 IMAD+LOP3 mix. */
 int vx_measure_peak(vx_ctx *ctx, int kind, double *tera_ops);
 
+/* Per-kernel-class device time, measured with CUDA events recorded on the
+ * launching stream around every launch while timing is on.  vx_get_timing
+ * waits for the recorded work, returns the summed milliseconds and launch
+ * counts per class since the last call, and resets them. */
+enum {
+    VX_K_FILL = 0,      /* noise fill of full chunks            */
+    VX_K_HALO = 1,      /* noise fill of halo slabs             */
+    VX_K_RESOLVE = 2,   /* neighbour hash insert + lookup       */
+    VX_K_COUNT = 3,     /* face count per chunk                 */
+    VX_K_SCAN = 4,      /* exclusive scan of the counts         */
+    VX_K_EMIT = 5,      /* instance emission                    */
+    VX_K_PACK = 6,      /* block ids -> bit planes              */
+    VX_K_FRUSTUM = 7,   /* AABB x plane test                    */
+    VX_K_COUNT_KINDS = 8
+};
+int vx_set_timing(vx_ctx *ctx, int on);
+int vx_get_timing(vx_ctx *ctx, double ms[VX_K_COUNT_KINDS], uint64_t launches[VX_K_COUNT_KINDS]);
+
 #ifdef __cplusplus
 }
 #endif

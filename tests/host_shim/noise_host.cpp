@@ -1,0 +1,37 @@
+// Host build of the DEVICE noise header (csrc/vx_noise.cuh) for CPU testing:
+// the CUDA intrinsics are mapped to plain separately-rounded f32 ops
+// (compile with -ffp-contract=off).  Test infrastructure only.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline int __float2int_rz(float f) { return (int)f; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#include "../../wgpu-voxel-engine_b200/csrc/vx_noise.cuh"
+
+// same coordinate construction and hoisting as vx_fill_kernel (kernels_fill.cu)
+extern "C" void shim_noise_chunk(const int32_t *c, int32_t seed, float freq, float gain, float lac, int oct,
+                                 float *out)
+{
+    const float ox = (float)(int32_t)((uint32_t)c[0] * 32u);
+    const float oy = (float)(int32_t)((uint32_t)c[2] * 32u);
+    const float oz = (float)(int32_t)((uint32_t)c[1] * 32u);
+    for (int zz = 0; zz < 32; ++zz)
+        for (int lane = 0; lane < 32; ++lane) {
+            const float sx = ox + (float)lane, sy = oy + (float)zz;
+            for (int y = 0; y < 32; ++y) {
+                float x = sx * freq, yy = sy * freq, z = (oz + (float)y) * freq, amp = 1.0f;
+                float r = vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed);
+                for (int o = 1; o < oct; ++o) {
+                    x *= lac; yy *= lac; z *= lac; amp *= gain;
+                    r = vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed) * amp + r;
+                }
+                out[lane + 32 * zz + 1024 * y] = r;
+            }
+        }
+}

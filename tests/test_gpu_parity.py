@@ -94,9 +94,13 @@ def test_mesh_checkerboard_worst_case(ctx, oracle):
     g = np.indices((32, 32, 32)).sum(axis=0) & 1
     cb = np.where(g == 0, 0, 2).astype(np.uint8).reshape(-1)
     coords = np.array([(0, 0, 0), (1, 0, 0)], np.int32)
-    blocks = np.stack([cb, np.where(g == 1, 1, 2).astype(np.uint8).reshape(-1)])
+    # the checkerboard continues across the chunk border (32 is even), second chunk is DIRT
+    blocks = np.stack([cb, np.where(g == 0, 1, 2).astype(np.uint8).reshape(-1)])
     got = ctx.mesh(coords, blocks)                       # neighbours resolved by coordinate
-    assert got.counts.tolist() == [98304, 98304]
+    assert got.counts.tolist() == [98304, 98304]         # SURVEY 8d config 4(i)
+    # opposite parity next door hides the 512 border faces on each side
+    anti = np.stack([cb, np.where(g == 1, 1, 2).astype(np.uint8).reshape(-1)])
+    assert ctx.mesh(coords, anti, instances=False).counts.tolist() == [97792, 97792]
     want = oracle.mesh_batch(coords, blocks, np.array([[-1, 1, -1, -1], [0, -1, -1, -1]], np.int32))
     assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
 

@@ -72,6 +72,8 @@ SIGNATURES = {
     "vx_frustum_cull_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "vx_sync": (_i, [_vp]),
     "vx_measure_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
+    "vx_set_timing": (_i, [_vp, _i]),
+    "vx_get_timing": (_i, [_vp, _vp, _vp]),
 }
 
 

@@ -233,6 +233,18 @@ class Context:
         check(self._L.vx_frustum_cull_device(self._h, planes_ptr, n_frames, coords_ptr, n, visible_ptr, bits_ptr,
                                              stream))
 
+    KERNEL_KINDS = ("fill", "halo", "resolve", "count", "scan", "emit", "pack", "frustum")
+
+    def set_timing(self, on: bool):
+        check(self._L.vx_set_timing(self._h, int(on)))
+
+    def get_timing(self) -> dict:
+        """{kind: (total_ms, launches)} since the last call (CUDA events on the launching stream)."""
+        ms = (C.c_double * 8)()
+        ln = (C.c_uint64 * 8)()
+        check(self._L.vx_get_timing(self._h, C.addressof(ms), C.addressof(ln)))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.KERNEL_KINDS)}
+
     def measure_peak(self, kind: int) -> float:
         v = C.c_double(0)
         check(self._L.vx_measure_peak(self._h, kind, C.byref(v)))

@@ -87,11 +87,49 @@ struct Dev {
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     uint64_t launches = 0;
+    // optional per-kernel-class CUDA-event timing (vx_set_timing)
+    bool timing = false;
+    struct Stamp { cudaEvent_t a, b; int kind; };
+    std::vector<Stamp> stamps;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_events;
     // `small` layout (bytes): 0 status u32 | 4 halo_count u32 | 8 near_zero u64
     uint32_t *st() const { return small.as<uint32_t>(); }
     uint32_t *halo_count() const { return small.as<uint32_t>() + 1; }
     unsigned long long *near() const { return reinterpret_cast<unsigned long long *>(small.as<uint8_t>() + 8); }
 };
+
+// records a CUDA-event pair around one kernel class on the launching stream
+struct TimerScope {
+    Dev &d;
+    cudaStream_t s;
+    Dev::Stamp st{nullptr, nullptr, 0};
+    TimerScope(Dev &dev, cudaStream_t stream, int kind) : d(dev), s(stream)
+    {
+        if (!d.timing) return;
+        if (d.free_events.empty()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess) return;
+            if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return; }
+            d.free_events.emplace_back(a, b);
+        }
+        st.a = d.free_events.back().first;
+        st.b = d.free_events.back().second;
+        st.kind = kind;
+        d.free_events.pop_back();
+        cudaEventRecord(st.a, s);
+    }
+    ~TimerScope()
+    {
+        if (!st.a) return;
+        cudaEventRecord(st.b, s);
+        d.stamps.push_back(st);
+    }
+};
+#define TIMED(dev, stream, kind, call)       \
+    do {                                     \
+        TimerScope ts_(dev, stream, kind);   \
+        CK(call);                            \
+    } while (0)
 
 }  // namespace
 
@@ -143,7 +181,7 @@ int dev_resolve(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_
     r.nbr = d.nbr.as<int32_t>();
     r.halo_items = allow_halo ? d.halo_items.as<vx_halo_item>() : nullptr;
     r.halo_count = d.halo_count();
-    CK(vx_launch_resolve(r, s, &d.launches));
+    TIMED(d, s, VX_K_RESOLVE, vx_launch_resolve(r, s, &d.launches));
     return VX_OK;
 }
 
@@ -164,7 +202,7 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     f.p = p;
     f.occ = d.occ.as<uint32_t>();
     f.blocks = d_blocks;
-    CK(vx_launch_fill(f, false, s, &d.launches));
+    TIMED(d, s, VX_K_FILL, vx_launch_fill(f, false, s, &d.launches));
     if (may_halo) {
         vx_fill_args h{};
         h.halo_items = d.halo_items.as<vx_halo_item>();
@@ -172,7 +210,7 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
         h.max_units = n * 4u;
         h.p = p;
         h.occ = d.halo.as<uint32_t>();
-        CK(vx_launch_fill(h, true, s, &d.launches));
+        TIMED(d, s, VX_K_HALO, vx_launch_fill(h, true, s, &d.launches));
     }
     vx_mesh_args m{};
     m.occ = d.occ.as<uint32_t>();
@@ -183,8 +221,8 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     m.counts = d_counts;
     m.offsets = d_offsets;
     m.n = n;
-    CK(vx_launch_mesh_count(m, s, &d.launches));
-    CK(vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));
+    TIMED(d, s, VX_K_SCAN, vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
     return VX_OK;
 }
 
@@ -224,7 +262,7 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
             m.m0 = a;
             m.quad_base = h_off[a];
             m.status = d.st();
-            CK(vx_launch_mesh_emit(m, b - a, d.stream, &d.launches));
+            TIMED(d, d.stream, VX_K_EMIT, vx_launch_mesh_emit(m, b - a, d.stream, &d.launches));
             CK(cudaEventRecord(d.emit_done[buf], d.stream));
             CK(cudaStreamWaitEvent(d.copy, d.emit_done[buf], 0));
             CK(cudaMemcpyAsync(h_out + h_off[a], d.inst[buf].p, q * sizeof(vx_instance), cudaMemcpyDeviceToHost,
@@ -337,6 +375,11 @@ void vx_destroy(vx_ctx *ctx)
                           &d.vis, &d.bits, &d.mesh_mask})
             b->release();
         if (d.h_small) cudaFreeHost(d.h_small);
+        for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
+        for (auto &ev : d.free_events) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
         for (int b = 0; b < 2; ++b) {
             if (d.emit_done[b]) cudaEventDestroy(d.emit_done[b]);
             if (d.d2h_done[b]) cudaEventDestroy(d.d2h_done[b]);
@@ -410,7 +453,7 @@ int vx_fill_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_
     f.noise = noise_out;
     f.near_zero = reinterpret_cast<unsigned long long *>(near_zero_out);
     if (near_zero_out) CK(cudaMemsetAsync(near_zero_out, 0, 8, s));
-    CK(vx_launch_fill(f, false, s, &d.launches));
+    TIMED(d, s, VX_K_FILL, vx_launch_fill(f, false, s, &d.launches));
     return VX_OK;
 }
 
@@ -451,7 +494,7 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
             f.blocks = blocks_out ? d.blocks.as<uint8_t>() : nullptr;
             f.noise = noise_out ? d.noise.as<float>() : nullptr;
             f.near_zero = near_zero_out ? d.near() : nullptr;
-            CK(vx_launch_fill(f, false, d.stream, &d.launches));
+            TIMED(d, d.stream, VX_K_FILL, vx_launch_fill(f, false, d.stream, &d.launches));
             const size_t g = lo + a;
             if (blocks_out)
                 CK(cudaMemcpyAsync(blocks_out + g * VX_VOXELS, d.blocks.p, c * VX_VOXELS, cudaMemcpyDeviceToHost,
@@ -486,16 +529,16 @@ static int mesh_prepare(Dev &d, cudaStream_t s, const int32_t *d_coords, uint32_
 {
     CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
     CK(d.typ.ensure((size_t)n * VX_ROWS * 4));
-    CK(vx_launch_pack(d_blocks, n, d.occ.as<uint32_t>(), d.typ.as<uint32_t>(), d_status, s, &d.launches));
+    TIMED(d, s, VX_K_PACK, vx_launch_pack(d_blocks, n, d.occ.as<uint32_t>(), d.typ.as<uint32_t>(), d_status, s, &d.launches));
     if (d_nbr_idx) {
         CK(d.nbr.ensure((size_t)n * 16));
-        CK(vx_launch_remap_nbr(d_nbr_idx, d.nbr.as<int32_t>(), n, s, &d.launches));
+        TIMED(d, s, VX_K_RESOLVE, vx_launch_remap_nbr(d_nbr_idx, d.nbr.as<int32_t>(), n, s, &d.launches));
     } else {
         RET(dev_resolve(d, s, d_coords, n, 0, n, nullptr, false));
     }
     vx_mesh_args m = emit_args(d, d_coords, d.typ.as<uint32_t>(), d_mesh_mask, d_counts, d_offsets, n);
-    CK(vx_launch_mesh_count(m, s, &d.launches));
-    CK(vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));
+    TIMED(d, s, VX_K_SCAN, vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
     return VX_OK;
 }
 
@@ -521,7 +564,7 @@ int vx_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *
         m.out = instances;
         m.capacity = capacity;
         m.status = status;
-        CK(vx_launch_mesh_emit(m, (uint32_t)n, s, &d.launches));
+        TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, (uint32_t)n, s, &d.launches));
     }
     return VX_OK;
 }
@@ -610,7 +653,7 @@ int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_no
         m.out = instances;
         m.capacity = capacity;
         m.status = status;
-        CK(vx_launch_mesh_emit(m, nn, s, &d.launches));
+        TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
     }
     return VX_OK;
 }
@@ -726,7 +769,7 @@ int vx_frustum_cull_device(vx_ctx *ctx, const float *planes, size_t n_frames, co
     Dev &d = ctx->devs[0];
     CK(cudaSetDevice(d.id));
     cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
-    CK(vx_launch_frustum(planes, (uint32_t)n_frames, coords, (uint32_t)n, visible, bits, s, &d.launches));
+    TIMED(d, s, VX_K_FRUSTUM, vx_launch_frustum(planes, (uint32_t)n_frames, coords, (uint32_t)n, visible, bits, s, &d.launches));
     return VX_OK;
 }
 
@@ -757,9 +800,10 @@ static int frustum_host(vx_ctx *ctx, const float *planes, size_t n_frames, const
         else CK(d.bits.ensure(fs * cw * 4));
         for (size_t f = 0; f < n_frames; f += fs) {
             const size_t nf = std::min(fs, n_frames - f);
-            CK(vx_launch_frustum(d.planes.as<float>() + f * 24, (uint32_t)nf, d.coords.as<int32_t>(), (uint32_t)c,
-                                 visible ? d.vis.as<uint8_t>() : nullptr, visible ? nullptr : d.bits.as<uint32_t>(),
-                                 d.stream, &d.launches));
+            TIMED(d, d.stream, VX_K_FRUSTUM,
+                  vx_launch_frustum(d.planes.as<float>() + f * 24, (uint32_t)nf, d.coords.as<int32_t>(), (uint32_t)c,
+                                    visible ? d.vis.as<uint8_t>() : nullptr,
+                                    visible ? nullptr : d.bits.as<uint32_t>(), d.stream, &d.launches));
             if (visible)
                 CK(cudaMemcpy2DAsync(visible + f * n + lo, n, d.vis.p, c, c, nf, cudaMemcpyDeviceToHost, d.stream));
             else
@@ -786,6 +830,37 @@ int vx_frustum_cull_bits(vx_ctx *ctx, const float *planes, size_t n_frames, cons
 }
 
 // ---------------------------------------------------------------------------
+int vx_set_timing(vx_ctx *ctx, int on)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (Dev &d : ctx->devs) d.timing = on != 0;
+    return VX_OK;
+}
+
+int vx_get_timing(vx_ctx *ctx, double ms[VX_K_COUNT_KINDS], uint64_t launches[VX_K_COUNT_KINDS])
+{
+    if (!ctx || !ms || !launches) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int k = 0; k < VX_K_COUNT_KINDS; ++k) {
+        ms[k] = 0.0;
+        launches[k] = 0;
+    }
+    for (Dev &d : ctx->devs) {
+        CK(cudaSetDevice(d.id));
+        for (const Dev::Stamp &st : d.stamps) {
+            CK(cudaEventSynchronize(st.b));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, st.a, st.b));
+            ms[st.kind] += t;
+            launches[st.kind] += 1;
+            d.free_events.emplace_back(st.a, st.b);
+        }
+        d.stamps.clear();
+    }
+    return VX_OK;
+}
+
 int vx_measure_peak(vx_ctx *ctx, int kind, double *tera_ops)
 {
     if (!ctx || !tera_ops) return fail(VX_ERR_BAD_ARG, "NULL argument");

@@ -20,9 +20,9 @@ __device__ __forceinline__ float vxn_grad(uint32_t h, float x, float y, float z)
     h = ((h * h) * 60493u) * h;
     h = (uint32_t)(((int32_t)h) >> 13) ^ h;
     // h13 = h & 13:  h13 < 8  <=> bit 3 clear;  h13 < 2 <=> bits 2,3 clear;
-    // h13 == 12 <=> bits 2,3 set (bit 0 is free in all three tests)
+    // h13 == 12 <=> bits 2,3 set and bit 0 clear
     const float u = (h & 8u) ? y : x;
-    const float v = ((h & 12u) == 0u) ? y : (((~h) & 12u) == 0u ? x : z);
+    const float v = ((h & 12u) == 0u) ? y : ((h & 13u) == 12u ? x : z);
     const float su = __uint_as_float(__float_as_uint(u) ^ (h << 31));
     const float sv = __uint_as_float(__float_as_uint(v) ^ ((h << 30) & 0x80000000u));
     return __fadd_rn(su, sv);

@@ -147,8 +147,9 @@ int vx_frustum_cull_bits(vx_ctx *ctx, const float *planes, size_t n_frames,
 
 /* ---- device-resident variants --------------------------------------------
  * Same semantics; every pointer is DEVICE memory on the context's first GPU,
- * work is enqueued on `stream` (a cudaStream_t, NULL = the context's stream)
- * and the call returns without synchronising.  Capacity overflow cannot be
+ * work is enqueued on `stream` (a cudaStream_t; NULL = the context's own
+ * stream -- pass cudaStreamLegacy / cudaStreamPerThread to name a default
+ * stream explicitly) and the call returns without synchronising.  Capacity overflow cannot be
  * reported synchronously: status[0] (device uint32, optional) gets bit 0 set,
  * bit 1 = bad block id.  Scratch lives in the context and is valid until the
  * next call on it. */

@@ -266,7 +266,9 @@ def test_device_resident_api(ctx, vox):
     cap = host.total + 10
     d_inst = torch.zeros(cap * 17, dtype=torch.int32, device=dev)
     d_status = torch.zeros(4, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)        # handle 0 would mean "the context's stream"
+    stream = tstream.cuda_stream
+    tstream.wait_stream(torch.cuda.current_stream())
     ctx.gen_mesh_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_offsets.data_ptr(), d_inst.data_ptr(), cap,
                         status_ptr=d_status.data_ptr(), stream=stream)
     torch.cuda.synchronize()

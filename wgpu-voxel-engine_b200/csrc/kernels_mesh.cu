@@ -20,7 +20,6 @@
 namespace {
 
 constexpr int kMeshThreads = 256;           // 4 consecutive rows per thread
-constexpr int kWindow = 4096;               // quad descriptors staged per pass
 
 // ---------------------------------------------------------------------------
 // bytes -> bit planes (vx_mesh with caller-provided Vec<Cube>)
@@ -324,16 +323,36 @@ __constant__ uint32_t c_tex[2][6] = {
     /* DIRT  [1,1,1,1,1,1] */ {1, 1, 1, 1, 1, 1},
 };
 
+constexpr int kEmitThreads = 256;            // one staged instance per thread per tile
+constexpr int kEmitWarps = kEmitThreads / 32;
+constexpr int kDescWindow = 2048;            // quad descriptors generated per pass
+constexpr int kLutStride = 20;               // words per LUT row (80 B: 16-B aligned, bank-spread)
+constexpr int kStageWords = kEmitThreads * 17 + 4;   // one tile + alignment lead
+
 struct EmitSmem {
     ChunkSmem c;
-    uint32_t typ[VX_ROWS];
-    uint32_t desc[kWindow];
-    uint32_t lut[16][17];         // [type*8 + face][word]
-    uint32_t pos[3][32];          // f32 bits of world x / y / z per local coordinate
-    uint32_t warp_tot[kMeshThreads / 32];
+    uint32_t rowbase[VX_ROWS + 1];           // exclusive scan of the per-row quad counts
+    uint32_t desc[kDescWindow];
+    __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
+    uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
+    uint32_t warp_tot[kEmitWarps];
+    __align__(16) uint32_t stage[2][kStageWords];
 };
 
-__global__ void __launch_bounds__(kMeshThreads)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// TMA 1-D bulk store shared -> global (sm_90+): 16-B aligned addresses, size % 16 == 0
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -350,98 +369,139 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     const uint32_t count = a.counts[m];
     if (count == 0) return;                      // also covers mesh_mask == 0
 
-    // constant tables -> shared (conflict-free per-lane lookups later)
-    for (uint32_t i = tid; i < 16 * 17; i += kMeshThreads) {
-        const uint32_t tf = i / 17, w = i - tf * 17, type = tf >> 3, face = tf & 7u;
+    // constant tables -> shared
+    for (uint32_t i = tid; i < 16 * kLutStride; i += kEmitThreads) {
+        const uint32_t tf = i / kLutStride, w = i - tf * kLutStride, type = tf >> 3, face = tf & 7u;
         uint32_t v = 0;
         if (face < 6) {
             if (w < 12) v = c_rot[face][w];
-            else if (w == 15) v = VX_1;
             else if (w == 16) v = c_tex[type][face];
         }
-        s.lut[tf][w] = v;
+        s.lut[i] = v;
     }
     if (tid < 96) {
         // coordinate.rs:60-65 + chunk.rs:66,68,76 + quad.rs:42: (chunk*32 + local) as f32
         const uint32_t axis = tid >> 5, v = tid & 31u;
-        const uint32_t c = (uint32_t)a.coords[3 * m + (axis == 0 ? 0 : (axis == 1 ? 1 : 2))];
+        const uint32_t c = (uint32_t)a.coords[3 * m + axis];
         s.pos[axis][v] = __float_as_uint((float)(int32_t)(c * 32u + v));
     }
-    if (a.typ) {
-        for (uint32_t r = tid; r < VX_ROWS; r += kMeshThreads) s.typ[r] = __ldg(a.typ + (size_t)m * VX_ROWS + r);
-    }
-    stage_chunk<kMeshThreads>(s.c, a, m);        // ends with __syncthreads()
+    stage_chunk<kEmitThreads>(s.c, a, m);        // ends with __syncthreads()
 
-    // per-thread: 4 consecutive rows, exclusive scan of row counts in row order
-    RowFaces rf[4];
-    uint32_t cnt[4], mine = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        rf[j] = row_faces(s.c, tid * 4 + j);
-        cnt[j] = row_count(rf[j]);
-        mine += cnt[j];
-    }
-    uint32_t inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(VX_FULL, inc, d);
-        if (lane >= (uint32_t)d) inc += t;
-    }
-    if (lane == 31) s.warp_tot[wid] = inc;
-    __syncthreads();
-    uint32_t row_base = inc - mine;
-#pragma unroll
-    for (uint32_t w = 0; w < kMeshThreads / 32; ++w)
-        if (w < wid) row_base += s.warp_tot[w];
-
-    uint32_t *out32 = reinterpret_cast<uint32_t *>(a.out) + (size_t)(a.offsets[m] - a.quad_base) * 17u;
-
-    for (uint32_t w0 = 0; w0 < count; w0 += kWindow) {
-        // --- descriptors of quads [w0, w0 + kWindow) in emission order -------------
-        uint32_t k = row_base;
+    // ---- per-row quad counts -> exclusive scan in row order ---------------------------
+    {
+        uint32_t cnt[4], mine = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t r = tid * 4 + j;
-            if (k + cnt[j] > w0 && k < w0 + kWindow) {
-                uint32_t any = rf[j].m[0] | rf[j].m[1] | rf[j].m[2] | rf[j].m[3] | rf[j].m[4] | rf[j].m[5];
-                const uint32_t tw = a.typ ? s.typ[r] : 0u;
-                uint32_t kk = k;
-                while (any) {
-                    const uint32_t x = __ffs(any) - 1;
-                    any &= any - 1;
-                    // descriptor: bits 0-14 voxel idx (x + 32 z + 1024 y), 15-17 face, 18 type
-                    const uint32_t base = (r << 5) | x | (((tw >> x) & 1u) << 18);
+            cnt[j] = row_count(row_faces(s.c, tid * 4 + j));
+            mine += cnt[j];
+        }
+        uint32_t inc = mine;
 #pragma unroll
-                    for (uint32_t f = 0; f < 6; ++f) {
-                        if ((rf[j].m[f] >> x) & 1u) {
-                            const uint32_t slot = kk - w0;
-                            if (slot < (uint32_t)kWindow) s.desc[slot] = base | (f << 15);
-                            ++kk;
-                        }
-                    }
-                }
-            }
-            k += cnt[j];
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(VX_FULL, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
         }
+        if (lane == 31) s.warp_tot[wid] = inc;
         __syncthreads();
-        // --- expansion: 17 words per quad, fully coalesced 32-bit stores ---------
-        const uint32_t nq = min((uint32_t)kWindow, count - w0);
-        const uint32_t nwords = nq * 17u;
-        uint32_t *dst = out32 + (size_t)w0 * 17u;
-        for (uint32_t i = tid; i < nwords; i += kMeshThreads) {
-            const uint32_t q = i / 17u, c = i - q * 17u;
-            const uint32_t d = s.desc[q];
-            uint32_t v = s.lut[(d >> 15) & 15u][c];
-            const uint32_t ax = c - 12u;
-            if (ax < 3u) {
-                // word 12: x (bits 0-4), 13: y (bits 10-14), 14: z (bits 5-9)
-                const uint32_t sh = (0x050a00u >> (8u * ax)) & 0xffu;
-                v = s.pos[ax][(d >> sh) & 31u];
-            }
-            dst[i] = v;
+        uint32_t base = inc - mine;
+#pragma unroll
+        for (uint32_t w = 0; w < (uint32_t)kEmitWarps; ++w)
+            if (w < wid) base += s.warp_tot[w];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            s.rowbase[tid * 4 + j] = base;
+            base += cnt[j];
         }
+        if (tid == kEmitThreads - 1) s.rowbase[VX_ROWS] = base;
         __syncthreads();
     }
+
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(a.out);
+    const unsigned long long chunk_word0 = (a.offsets[m] - a.quad_base) * 17ull;   // first word of this chunk
+    const bool out_aligned = (reinterpret_cast<unsigned long long>(out32) & 15ull) == 0;
+    const uint32_t *typ_rows = a.typ ? a.typ + (size_t)m * VX_ROWS : nullptr;
+    uint32_t tile = 0;
+
+    for (uint32_t d0 = 0; d0 < count; d0 += kDescWindow) {
+        // ---- descriptors of quads [d0, d0 + kDescWindow) in emission order; one warp per row,
+        //      lane = x, so every lane handles at most 6 quads (balanced) -----------------------
+        const uint32_t d1 = d0 + kDescWindow;
+        // first row whose range reaches past d0: lower bound over rowbase[r + 1] > d0
+        uint32_t lo = 0, hi = VX_ROWS;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s.rowbase[mid + 1] > d0) hi = mid; else lo = mid + 1;
+        }
+        for (uint32_t r = lo + wid; r < VX_ROWS; r += kEmitWarps) {
+            const uint32_t rb = s.rowbase[r];
+            if (rb >= d1) break;
+            if (s.rowbase[r + 1] == rb) continue;
+            const RowFaces f = row_faces(s.c, r);
+            const uint32_t fs = ((f.m[0] >> lane) & 1u) | (((f.m[1] >> lane) & 1u) << 1) |
+                                (((f.m[2] >> lane) & 1u) << 2) | (((f.m[3] >> lane) & 1u) << 3) |
+                                (((f.m[4] >> lane) & 1u) << 4) | (((f.m[5] >> lane) & 1u) << 5);
+            const uint32_t c = __popc(fs);
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t pre = __popc(__ballot_sync(VX_FULL, c & 1u) & lt) +
+                                 2u * __popc(__ballot_sync(VX_FULL, c & 2u) & lt) +
+                                 4u * __popc(__ballot_sync(VX_FULL, c & 4u) & lt);
+            uint32_t k = rb + pre - d0;          // wraps for quads before the window; fixed by ++k
+            const uint32_t tbit = typ_rows ? ((__ldg(typ_rows + r) >> lane) & 1u) : 0u;
+            // descriptor: bits 0-14 voxel idx (x + 32 z + 1024 y), 15-17 face, 18 type
+            const uint32_t dbase = (r << 5) | lane | (tbit << 18);
+#pragma unroll
+            for (uint32_t face = 0; face < 6; ++face) {
+                if ((fs >> face) & 1u) {
+                    if (k < (uint32_t)kDescWindow) s.desc[k] = dbase | (face << 15);
+                    ++k;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- tiles of kEmitThreads instances: build in shared, leave through TMA ------------
+        const uint32_t nd = min((uint32_t)kDescWindow, count - d0);
+        for (uint32_t s0 = 0; s0 < nd; s0 += kEmitThreads, ++tile) {
+            uint32_t *stg = s.stage[tile & 1u];
+            // the bulk store that last read this buffer (two tiles ago) must be done reading
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            const uint32_t nq = min((uint32_t)kEmitThreads, nd - s0);
+            const unsigned long long G = chunk_word0 + (unsigned long long)(d0 + s0) * 17ull;
+            const uint32_t lead = (uint32_t)(G & 3ull);        // stage word i <-> global word G - lead + i
+            if (tid < nq) {
+                const uint32_t d = s.desc[s0 + tid];
+                const uint32_t tf = (d >> 15) & 15u;
+                const uint4 *L = reinterpret_cast<const uint4 *>(&s.lut[tf * kLutStride]);
+                const uint4 c0 = L[0], c1 = L[1], c2 = L[2];
+                uint32_t *w = stg + lead + tid * 17u;          // stride 17 words: conflict-free
+                w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
+                w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
+                w[8] = c2.x; w[9] = c2.y; w[10] = c2.z; w[11] = c2.w;
+                w[12] = s.pos[0][d & 31u];
+                w[13] = s.pos[1][(d >> 10) & 31u];
+                w[14] = s.pos[2][(d >> 5) & 31u];
+                w[15] = VX_1;
+                w[16] = s.lut[tf * kLutStride + 16];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+            __syncthreads();
+            const uint32_t nwords = nq * 17u;
+            // 16-B aligned body [Ga, Gb) goes out as one bulk store; the <= 3-word head and tail
+            // (or everything, if the caller's buffer is not 16-B aligned) as scalar stores
+            unsigned long long Ga = (G + 3ull) & ~3ull, Gb = (G + nwords) & ~3ull;
+            if (!out_aligned || Gb <= Ga) Ga = Gb = G;
+            if (tid == 0 && Gb > Ga)
+                bulk_store(out32 + Ga, stg + (uint32_t)(Ga - G) + lead, (uint32_t)(Gb - Ga) * 4u);
+            const uint32_t head = (uint32_t)(Ga - G), tail0 = (uint32_t)(Gb - G);
+            for (uint32_t i = tid; i < head + (nwords - tail0); i += kEmitThreads) {
+                const uint32_t wi = (i < head) ? i : tail0 + (i - head);
+                out32[G + wi] = stg[lead + wi];
+            }
+        }
+        __syncthreads();                         // desc[] is rewritten by the next window
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
 }
 
 }  // namespace
@@ -502,8 +562,17 @@ cudaError_t vx_launch_scan(const uint32_t *counts, uint64_t *offsets, uint32_t n
 cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches)
 {
     if (len == 0) return cudaSuccess;
-    static_assert(sizeof(EmitSmem) <= 48 * 1024, "emit kernel must fit the default dynamic smem limit");
-    vx_mesh_emit_kernel<<<len, kMeshThreads, sizeof(EmitSmem), s>>>(a);
+    static_assert(sizeof(EmitSmem) <= 64 * 1024, "emit kernel shared memory budget");
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(EmitSmem));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    vx_mesh_emit_kernel<<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -323,20 +323,18 @@ __constant__ uint32_t c_tex[2][6] = {
     /* DIRT  [1,1,1,1,1,1] */ {1, 1, 1, 1, 1, 1},
 };
 
-constexpr int kEmitThreads = 256;            // one staged instance per thread per tile
+constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
-constexpr int kDescWindow = 2048;            // quad descriptors generated per pass
 constexpr int kLutStride = 20;               // words per LUT row (80 B: 16-B aligned, bank-spread)
-constexpr int kStageWords = kEmitThreads * 17 + 4;   // one tile + alignment lead
+constexpr int kTileWords = 32 * 17 + 4;      // one warp tile (32 instances) + alignment lead
 
 struct EmitSmem {
     ChunkSmem c;
     uint32_t rowbase[VX_ROWS + 1];           // exclusive scan of the per-row quad counts
-    uint32_t desc[kDescWindow];
     __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
     uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
     uint32_t warp_tot[kEmitWarps];
-    __align__(16) uint32_t stage[2][kStageWords];
+    __align__(16) uint32_t stage[kEmitWarps][2][kTileWords];   // per-warp double-buffered tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -352,6 +350,14 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// Emission.  After the per-chunk setup (stage + row scan) there is no CTA-wide
+// barrier: each warp owns every kEmitWarps-th tile of 32 consecutive quads and
+// each lane decodes ITS quad independently --
+//   row   = binary search of the quad index in the row scan,
+//   cube  = bit-parallel select over 3-bit vertical counters of the six masks,
+//   face  = k-th set face bit of that cube,
+// builds the 68-byte InstanceRaw in the warp's staging tile (stride-17 words,
+// bank-conflict free) and the tile leaves through one TMA bulk store.
 __global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
 {
@@ -413,95 +419,87 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
             base += cnt[j];
         }
         if (tid == kEmitThreads - 1) s.rowbase[VX_ROWS] = base;
-        __syncthreads();
+        __syncthreads();                         // last CTA-wide barrier
     }
 
     uint32_t *out32 = reinterpret_cast<uint32_t *>(a.out);
     const unsigned long long chunk_word0 = (a.offsets[m] - a.quad_base) * 17ull;   // first word of this chunk
     const bool out_aligned = (reinterpret_cast<unsigned long long>(out32) & 15ull) == 0;
     const uint32_t *typ_rows = a.typ ? a.typ + (size_t)m * VX_ROWS : nullptr;
-    uint32_t tile = 0;
+    const uint32_t n_tiles = (count + 31u) >> 5;
+    uint32_t it = 0;
 
-    for (uint32_t d0 = 0; d0 < count; d0 += kDescWindow) {
-        // ---- descriptors of quads [d0, d0 + kDescWindow) in emission order; one warp per row,
-        //      lane = x, so every lane handles at most 6 quads (balanced) -----------------------
-        const uint32_t d1 = d0 + kDescWindow;
-        // first row whose range reaches past d0: lower bound over rowbase[r + 1] > d0
-        uint32_t lo = 0, hi = VX_ROWS;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s.rowbase[mid + 1] > d0) hi = mid; else lo = mid + 1;
-        }
-        for (uint32_t r = lo + wid; r < VX_ROWS; r += kEmitWarps) {
-            const uint32_t rb = s.rowbase[r];
-            if (rb >= d1) break;
-            if (s.rowbase[r + 1] == rb) continue;
-            const RowFaces f = row_faces(s.c, r);
-            const uint32_t fs = ((f.m[0] >> lane) & 1u) | (((f.m[1] >> lane) & 1u) << 1) |
-                                (((f.m[2] >> lane) & 1u) << 2) | (((f.m[3] >> lane) & 1u) << 3) |
-                                (((f.m[4] >> lane) & 1u) << 4) | (((f.m[5] >> lane) & 1u) << 5);
-            const uint32_t c = __popc(fs);
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t pre = __popc(__ballot_sync(VX_FULL, c & 1u) & lt) +
-                                 2u * __popc(__ballot_sync(VX_FULL, c & 2u) & lt) +
-                                 4u * __popc(__ballot_sync(VX_FULL, c & 4u) & lt);
-            uint32_t k = rb + pre - d0;          // wraps for quads before the window; fixed by ++k
-            const uint32_t tbit = typ_rows ? ((__ldg(typ_rows + r) >> lane) & 1u) : 0u;
-            // descriptor: bits 0-14 voxel idx (x + 32 z + 1024 y), 15-17 face, 18 type
-            const uint32_t dbase = (r << 5) | lane | (tbit << 18);
+    for (uint32_t tile = wid; tile < n_tiles; tile += kEmitWarps, ++it) {
+        uint32_t *stg = s.stage[wid][it & 1u];
+        // the bulk store that last read this buffer (two tiles ago) must be done reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+
+        const uint32_t q0 = tile << 5;
+        const uint32_t nq = min(32u, count - q0);
+        const unsigned long long G = chunk_word0 + (unsigned long long)q0 * 17ull;
+        const uint32_t lead = (uint32_t)(G & 3ull);            // stage word i <-> global word G - lead + i
+        if (lane < nq) {
+            const uint32_t q = q0 + lane;
+            // row: largest r with rowbase[r] <= q (empty rows tie; the last one is the owner)
+            uint32_t r = 0;
 #pragma unroll
-            for (uint32_t face = 0; face < 6; ++face) {
-                if ((fs >> face) & 1u) {
-                    if (k < (uint32_t)kDescWindow) s.desc[k] = dbase | (face << 15);
-                    ++k;
-                }
+            for (uint32_t step = 512; step > 0; step >>= 1)
+                if (s.rowbase[r + step] <= q) r += step;
+            uint32_t k = q - s.rowbase[r];
+            const RowFaces f = row_faces(s.c, r);
+            // 3-bit vertical counters: per x, c(x) = number of faces = s0 + 2 s1 + 4 s2
+            const uint32_t a0 = f.m[0] ^ f.m[1] ^ f.m[2], a1 = (f.m[0] & f.m[1]) | (f.m[2] & (f.m[0] ^ f.m[1]));
+            const uint32_t b0 = f.m[3] ^ f.m[4] ^ f.m[5], b1 = (f.m[3] & f.m[4]) | (f.m[5] & (f.m[3] ^ f.m[4]));
+            const uint32_t s0 = a0 ^ b0, c0 = a0 & b0;
+            const uint32_t s1 = a1 ^ b1 ^ c0, s2 = (a1 & b1) | (c0 & (a1 ^ b1));
+            // cube: largest x with (# quads of cubes < x) <= k
+            uint32_t x = 0, before = 0;
+#pragma unroll
+            for (uint32_t step = 16; step > 0; step >>= 1) {
+                const uint32_t lt = (1u << (x + step)) - 1u;
+                const uint32_t c = __popc(s0 & lt) + 2u * __popc(s1 & lt) + 4u * __popc(s2 & lt);
+                if (c <= k) { x += step; before = c; }
             }
+            k -= before;
+            // face: the k-th set face bit of cube x, in LEFT,RIGHT,BACK,FRONT,DOWN,UP order
+            uint32_t face = 0, seen = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < 6; ++g) {
+                const uint32_t bit = (f.m[g] >> x) & 1u;
+                if (bit && seen == k) face = g;
+                seen += bit;
+            }
+            const uint32_t type = typ_rows ? ((__ldg(typ_rows + r) >> x) & 1u) : 0u;
+            const uint32_t tf = type * 8u + face;
+            const uint4 *L = reinterpret_cast<const uint4 *>(&s.lut[tf * kLutStride]);
+            const uint4 c0v = L[0], c1v = L[1], c2v = L[2];
+            uint32_t *w = stg + lead + lane * 17u;             // stride 17 words: conflict-free
+            w[0] = c0v.x; w[1] = c0v.y; w[2] = c0v.z; w[3] = c0v.w;
+            w[4] = c1v.x; w[5] = c1v.y; w[6] = c1v.z; w[7] = c1v.w;
+            w[8] = c2v.x; w[9] = c2v.y; w[10] = c2v.z; w[11] = c2v.w;
+            w[12] = s.pos[0][x];
+            w[13] = s.pos[1][r >> 5];
+            w[14] = s.pos[2][r & 31u];
+            w[15] = VX_1;
+            w[16] = s.lut[tf * kLutStride + 16];
         }
-        __syncthreads();
-
-        // ---- tiles of kEmitThreads instances: build in shared, leave through TMA ------------
-        const uint32_t nd = min((uint32_t)kDescWindow, count - d0);
-        for (uint32_t s0 = 0; s0 < nd; s0 += kEmitThreads, ++tile) {
-            uint32_t *stg = s.stage[tile & 1u];
-            // the bulk store that last read this buffer (two tiles ago) must be done reading
-            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncthreads();
-            const uint32_t nq = min((uint32_t)kEmitThreads, nd - s0);
-            const unsigned long long G = chunk_word0 + (unsigned long long)(d0 + s0) * 17ull;
-            const uint32_t lead = (uint32_t)(G & 3ull);        // stage word i <-> global word G - lead + i
-            if (tid < nq) {
-                const uint32_t d = s.desc[s0 + tid];
-                const uint32_t tf = (d >> 15) & 15u;
-                const uint4 *L = reinterpret_cast<const uint4 *>(&s.lut[tf * kLutStride]);
-                const uint4 c0 = L[0], c1 = L[1], c2 = L[2];
-                uint32_t *w = stg + lead + tid * 17u;          // stride 17 words: conflict-free
-                w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
-                w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
-                w[8] = c2.x; w[9] = c2.y; w[10] = c2.z; w[11] = c2.w;
-                w[12] = s.pos[0][d & 31u];
-                w[13] = s.pos[1][(d >> 10) & 31u];
-                w[14] = s.pos[2][(d >> 5) & 31u];
-                w[15] = VX_1;
-                w[16] = s.lut[tf * kLutStride + 16];
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
-            __syncthreads();
-            const uint32_t nwords = nq * 17u;
-            // 16-B aligned body [Ga, Gb) goes out as one bulk store; the <= 3-word head and tail
-            // (or everything, if the caller's buffer is not 16-B aligned) as scalar stores
-            unsigned long long Ga = (G + 3ull) & ~3ull, Gb = (G + nwords) & ~3ull;
-            if (!out_aligned || Gb <= Ga) Ga = Gb = G;
-            if (tid == 0 && Gb > Ga)
-                bulk_store(out32 + Ga, stg + (uint32_t)(Ga - G) + lead, (uint32_t)(Gb - Ga) * 4u);
-            const uint32_t head = (uint32_t)(Ga - G), tail0 = (uint32_t)(Gb - G);
-            for (uint32_t i = tid; i < head + (nwords - tail0); i += kEmitThreads) {
-                const uint32_t wi = (i < head) ? i : tail0 + (i - head);
-                out32[G + wi] = stg[lead + wi];
-            }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+        __syncwarp();
+        const uint32_t nwords = nq * 17u;
+        // 16-B aligned body [Ga, Gb) leaves as one bulk store; the <= 3-word head and tail (or
+        // everything, if the caller's buffer is not 16-B aligned) as scalar stores
+        unsigned long long Ga = (G + 3ull) & ~3ull, Gb = (G + nwords) & ~3ull;
+        if (!out_aligned || Gb <= Ga) Ga = Gb = G;
+        if (lane == 0 && Gb > Ga)
+            bulk_store(out32 + Ga, stg + (uint32_t)(Ga - G) + lead, (uint32_t)(Gb - Ga) * 4u);
+        const uint32_t head = (uint32_t)(Ga - G), tail0 = (uint32_t)(Gb - G);
+        for (uint32_t i = lane; i < head + (nwords - tail0); i += 32u) {
+            const uint32_t wi = (i < head) ? i : tail0 + (i - head);
+            out32[G + wi] = stg[lead + wi];
         }
-        __syncthreads();                         // desc[] is rewritten by the next window
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
 }
 
 }  // namespace

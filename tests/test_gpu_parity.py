@@ -205,6 +205,28 @@ def test_gen_mesh_ring_32x32_properties(ctx, oracle):
     assert solid.any() and not solid.all()
 
 
+def test_fill_sign_only_shortcuts_are_exact(ctx, vox):
+    # the fast kernel skips octaves that cannot flip the sign; the exact kernel (noise output)
+    # evaluates everything: blocks must agree on every voxel, for the default terrain at
+    # BASELINE size and for parameters that move the octave amplitudes around
+    coords = _grid(-16, -16, 32, 32)
+    fast = ctx.fill(coords, blocks=True, occupancy=True)
+    slow = ctx.fill(coords, blocks=True, noise=True)
+    assert np.array_equal(fast["blocks"], slow["blocks"])
+    assert np.array_equal(fast["blocks"] == 0, slow["noise"] < 0)
+    bits = np.unpackbits(fast["occupancy"].view(np.uint8), axis=1, bitorder="little")
+    assert np.array_equal(bits.astype(bool), fast["blocks"] != 2)
+    rng = np.random.default_rng(3)
+    far = rng.integers(-200000, 200000, size=(48, 3)).astype(np.int32)
+    for gain, lac, freq, seed in [(2.5, 0.5, 0.09, 7), (0.5, 2.0, 0.03, 1), (1.0, 0.5, 0.2, 99), (-3.0, 0.7, 0.09, 5),
+                                  (40.0, 0.5, 0.09, 1)]:
+        p = vox.default_noise_params(gain=gain, lacunarity=lac, freq=freq, seed=seed)
+        a = ctx.fill(far, params=p, blocks=True)["blocks"]
+        b = ctx.fill(far, params=p, blocks=True, noise=True)
+        assert np.array_equal(a, b["blocks"]), (gain, lac, freq, seed)
+        assert np.array_equal(a == 0, b["noise"] < 0)
+
+
 def test_reference_interface_mirror(ctx, vox, oracle):
     # reads like the reference's call site chunk_builder.rs:80-84
     pos = vox.ChunkCoord3D(0, 0, 0)

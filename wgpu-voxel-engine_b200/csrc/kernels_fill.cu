@@ -132,6 +132,105 @@ vx_fill_kernel(const vx_fill_args a)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path (occupancy [+ block ids], 3 octaves): sign-only evaluation.
+//
+// Only the SIGN of the FBM sum reaches the blocks (chunk.rs:38), and
+// |simplex_3d| <= 1/32.69587 = 0.030585 for ANY hash outcome (the supremum of
+// sum_n t_n^4 * max_g |g . d_n| over the simplex cell; tests/ re-derives it
+// numerically).  With octave amplitudes 1, g, g^2 (perlin_noise.rs:16-18) the
+// low-frequency octaves dominate, so they are evaluated first:
+//   u = s3*g^2;            |u|     > B(1+|g|)  -> sign(r) = sign(u)      skip 2 octaves
+//   t = s2*g;              |u + t| > B         -> sign(r) = sign(u + t)  skip 1 octave
+//   otherwise r = u + (t + s1), the reference's exact association.
+// The skip is taken only when it holds for the whole warp (no divergence); a
+// warp owns a 4 x 4 x 2 voxel brick per step, which keeps ~52 % / ~11 % of the
+// steps on the one-/two-octave shortcuts for the default terrain (rows of 32
+// voxels along x: 11 % / 0 %).  Blocks stay bit-exact by construction.
+//
+// CTA = 8 warps = (chunk, 4-wide z block); warp = 4-wide x block; lane =
+// (x & 3) | (z & 3) << 2 | (y & 1) << 4; 16 steps walk y.  Ballot nibbles are
+// gathered in shared memory into the 128 row words of the CTA's z block.
+// ---------------------------------------------------------------------------
+template <bool WANT_BLOCKS>
+__global__ void __launch_bounds__(256)
+vx_fill_brick_kernel(const vx_fill_args a)
+{
+    __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
+    const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
+    const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
+    const float ox = (float)(int32_t)((uint32_t)cx * 32u);
+    const float oy = (float)(int32_t)((uint32_t)cz * 32u);
+    const float oz = (float)(int32_t)((uint32_t)cy * 32u);
+    const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
+    const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
+    const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const uint32_t seed = (uint32_t)a.p.seed;
+
+    float hx[3], hy[3], hxy[3];
+    hx[0] = __fmul_rn(sx, freq);
+    hy[0] = __fmul_rn(sy, freq);
+    hxy[0] = __fadd_rn(hx[0], hy[0]);
+#pragma unroll
+    for (int o = 1; o < 3; ++o) {
+        hx[o] = __fmul_rn(hx[o - 1], lac);
+        hy[o] = __fmul_rn(hy[o - 1], lac);
+        hxy[o] = __fadd_rn(hx[o], hy[o]);
+    }
+    const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+    const float thr1 = a.thr1, thr2 = a.thr2;
+
+#pragma unroll 1
+    for (uint32_t it = 0; it < 16u; ++it) {
+        const uint32_t y = 2u * it + yy;
+        const float z0 = __fmul_rn(__fadd_rn(oz, (float)y), freq);
+        const float z1 = __fmul_rn(z0, lac);
+        const float z2 = __fmul_rn(z1, lac);
+        const float u = __fmul_rn(vxn_simplex3(hx[2], hy[2], z2, hxy[2], seed), amp2);
+        bool solid;
+        if (__all_sync(VX_FULL, fabsf(u) > thr2)) {
+            solid = u < 0.0f;
+        } else {
+            const float t = __fmul_rn(vxn_simplex3(hx[1], hy[1], z1, hxy[1], seed), amp1);
+            const float ut = __fadd_rn(u, t);
+            if (__all_sync(VX_FULL, fabsf(ut) > thr1)) {
+                solid = ut < 0.0f;
+            } else {
+                const float s1 = vxn_simplex3(hx[0], hy[0], z0, hxy[0], seed);
+                // reference association: r = s1; r = t + r; r = u + r
+                solid = __fadd_rn(u, __fadd_rn(t, s1)) < 0.0f;
+            }
+        }
+        const uint32_t word = __ballot_sync(VX_FULL, solid);     // bit = yy*16 + zz*4 + xx
+        if (lane < 8u) nib[2u * it + (lane >> 2)][lane & 3u][xblk] = (uint8_t)((word >> (4u * lane)) & 15u);
+    }
+    __syncthreads();
+
+    // 128 row words of this z block: row (y, zblk*4 + zz) = 8 nibbles, one per x block
+    const uint32_t t = threadIdx.x;
+    const uint32_t rr = t >> 1, half = t & 1u;                  // row 0..127, 16-voxel half
+    const uint32_t y = rr >> 2, zq = rr & 3u;
+    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[y][zq][0]);
+    // pack the low nibble of each of the 8 bytes into one 32-bit word
+    const uint32_t lo = (nb.x & 0x0f0f0f0fu), hi = (nb.y & 0x0f0f0f0fu);
+    const uint32_t plo = (lo | (lo >> 4)) & 0x00ff00ffu, phi = (hi | (hi >> 4)) & 0x00ff00ffu;
+    const uint32_t w16lo = (plo | (plo >> 8)) & 0xffffu, w16hi = (phi | (phi >> 8)) & 0xffffu;
+    const uint32_t wordv = w16lo | (w16hi << 16);
+    if (half == 0) a.occ[(size_t)item * VX_ROWS + y * 32u + zblk * 4u + zq] = wordv;
+    if (WANT_BLOCKS) {
+        const uint32_t air16 = ~(wordv >> (16u * half)) & 0xffffu;
+        uint4 v;
+        v.x = (((air16 >> 0) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.y = (((air16 >> 4) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.z = (((air16 >> 8) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        *reinterpret_cast<uint4 *>(a.blocks + (size_t)item * VX_VOXELS + (size_t)y * 1024u +
+                                   (zblk * 4u + zq) * 32u + half * 16u) = v;
+    }
+}
+
 template <int OCT, bool HALO>
 cudaError_t launch_oct(const vx_fill_args &a, cudaStream_t s)
 {
@@ -168,7 +267,20 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
 {
     if (a.max_units == 0) return cudaSuccess;
     if (launches) ++*launches;
-    // octaves = 3 (perlin_noise.rs:18) gets the fully hoisted instantiation;
+    // octaves = 3 (perlin_noise.rs:18) without noise/census output: sign-only brick kernel
+    if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && !a.force_exact) {
+        vx_fill_args b = a;
+        // |simplex_3d| <= 0.030585; 0.0306 plus a relative slack far above the f32 rounding of u, t, u+t
+        const float g1 = fabsf(a.p.gain), g2 = fabsf(a.p.gain * a.p.gain);
+        const float slack = 1.0f + 1e-5f * (1.0f + g1 + g2);
+        b.thr1 = 0.0306f * slack;
+        b.thr2 = 0.0306f * (1.0f + g1) * slack;
+        const uint32_t n_items = a.max_units / 32u;
+        if (a.blocks) vx_fill_brick_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
+        else vx_fill_brick_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);
+        return cudaGetLastError();
+    }
+    // octaves = 3 otherwise gets the fully hoisted exact instantiation;
     // anything else runs the generic loop.
     if (a.p.octaves == 3)
         return halo_mode ? launch_oct<3, true>(a, s) : launch_oct<3, false>(a, s);

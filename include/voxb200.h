@@ -185,8 +185,8 @@ enum {
     VX_K_FILL = 0,      /* noise fill of full chunks            */
     VX_K_HALO = 1,      /* noise fill of halo slabs             */
     VX_K_RESOLVE = 2,   /* neighbour hash insert + lookup       */
-    VX_K_COUNT = 3,     /* face count per chunk                 */
-    VX_K_SCAN = 4,      /* exclusive scan of the counts         */
+    VX_K_COUNT = 3,     /* face count per chunk + exclusive scan (run by its last CTA) */
+    VX_K_SCAN = 4,      /* (unused: the scan is fused into VX_K_COUNT) */
     VX_K_EMIT = 5,      /* instance emission                    */
     VX_K_PACK = 6,      /* block ids -> bit planes              */
     VX_K_FRUSTUM = 7,   /* AABB x plane test                    */

@@ -92,9 +92,10 @@ struct Dev {
     struct Stamp { cudaEvent_t a, b; int kind; };
     std::vector<Stamp> stamps;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_events;
-    // `small` layout (bytes): 0 status u32 | 4 halo_count u32 | 8 near_zero u64
+    // `small` layout (bytes): 0 status u32 | 4 halo_count u32 | 8 near_zero u64 | 16 count-kernel ticket u32
     uint32_t *st() const { return small.as<uint32_t>(); }
     uint32_t *halo_count() const { return small.as<uint32_t>() + 1; }
+    uint32_t *ticket() const { return small.as<uint32_t>() + 4; }
     unsigned long long *near() const { return reinterpret_cast<unsigned long long *>(small.as<uint8_t>() + 8); }
 };
 
@@ -221,8 +222,8 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     m.counts = d_counts;
     m.offsets = d_offsets;
     m.n = n;
-    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));
-    TIMED(d, s, VX_K_SCAN, vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    m.ticket = d.ticket();
+    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));     // the last CTA also scans
     return VX_OK;
 }
 
@@ -537,8 +538,8 @@ static int mesh_prepare(Dev &d, cudaStream_t s, const int32_t *d_coords, uint32_
         RET(dev_resolve(d, s, d_coords, n, 0, n, nullptr, false));
     }
     vx_mesh_args m = emit_args(d, d_coords, d.typ.as<uint32_t>(), d_mesh_mask, d_counts, d_offsets, n);
-    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));
-    TIMED(d, s, VX_K_SCAN, vx_launch_scan(d_counts, d_offsets, n, s, &d.launches));
+    m.ticket = d.ticket();
+    TIMED(d, s, VX_K_COUNT, vx_launch_mesh_count(m, s, &d.launches));     // the last CTA also scans
     return VX_OK;
 }
 

@@ -133,6 +133,73 @@ __global__ void vx_resolve_kernel(const vx_resolve_args a)
     a.nbr[t] = ref;
 }
 
+// Small lists (<= kSmallResolve chunks): one CTA builds the hash table in shared
+// memory and answers the lookups in the same launch (no memsets, no second kernel).
+constexpr uint32_t kSmallResolve = 4096;
+
+__device__ __forceinline__ int32_t lookup_in(const int32_t *table, uint32_t mask, const int32_t *coords,
+                                             int32_t x, int32_t y, int32_t z)
+{
+    uint32_t s = coord_hash(x, y, z) & mask;
+    for (;;) {
+        const int32_t j = table[s];
+        if (j < 0) return -1;
+        if (coords[3 * j] == x && coords[3 * j + 1] == y && coords[3 * j + 2] == z) return j;
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(1024) vx_resolve_small_kernel(const vx_resolve_args a)
+{
+    // dynamic shared memory: int32 table[table_size] | int32 coords[3 * n]
+    extern __shared__ int32_t rs_smem[];
+    __shared__ uint32_t halo_n;
+    int32_t *table = rs_smem;
+    int32_t *co = rs_smem + a.table_size;
+    const uint32_t mask = a.table_size - 1u;
+    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) table[i] = -1;
+    for (uint32_t i = threadIdx.x; i < 3u * a.n; i += blockDim.x) co[i] = __ldg(a.coords + i);
+    if (threadIdx.x == 0) halo_n = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+        const int32_t x = co[3 * i], y = co[3 * i + 1], z = co[3 * i + 2];
+        uint32_t s = coord_hash(x, y, z) & mask;
+        for (;;) {
+            const int32_t prev = atomicCAS(&table[s], -1, (int32_t)i);
+            if (prev == -1) break;
+            if (co[3 * prev] == x && co[3 * prev + 1] == y && co[3 * prev + 2] == z) {
+                atomicMin(&table[s], (int32_t)i);      // duplicates: the smallest index answers lookups
+                break;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < (a.hi - a.lo) * 4u; t += blockDim.x) {
+        const uint32_t i = a.lo + (t >> 2), k = t & 3u;
+        int32_t ref = VX_NBR_NONE;
+        const bool wanted = a.nbr_mask ? ((a.nbr_mask[i] >> k) & 1u) : true;
+        if (wanted) {
+            const int32_t x = (int32_t)((uint32_t)co[3 * i] + (k == 0 ? 0xffffffffu : (k == 1 ? 1u : 0u)));
+            const int32_t y = co[3 * i + 1];
+            const int32_t z = (int32_t)((uint32_t)co[3 * i + 2] + (k == 2 ? 0xffffffffu : (k == 3 ? 1u : 0u)));
+            const int32_t j = lookup_in(table, mask, co, x, y, z);
+            bool present = a.nbr_mask != nullptr || j >= 0;
+            if (j >= 0 && (uint32_t)j >= a.lo && (uint32_t)j < a.hi) ref = j - (int32_t)a.lo;
+            if (ref < 0 && present && a.halo_items) {
+                const uint32_t slot = atomicAdd(&halo_n, 1u);
+                vx_halo_item it;
+                it.cx = x; it.cy = y; it.cz = z; it.kind = (int32_t)k;
+                a.halo_items[slot] = it;
+                ref = vx_halo_ref((int)slot);
+            }
+        }
+        a.nbr[t] = ref;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.halo_count) *a.halo_count = halo_n;
+}
+
 // caller-provided nbr_idx (>= 0 index, anything negative = None)
 __global__ void vx_remap_nbr_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, uint32_t n4)
 {
@@ -225,6 +292,58 @@ __device__ __forceinline__ uint32_t row_count(const RowFaces &f)
 }
 
 // ---------------------------------------------------------------------------
+// exclusive scan of the counts -> uint64 offsets[n+1], run by ONE CTA of
+// kMeshThreads threads: the last CTA of the count kernel to finish (ticket).
+// ---------------------------------------------------------------------------
+__device__ void scan_counts_cta(const uint32_t *counts, uint64_t *offsets, uint32_t n)
+{
+    __shared__ unsigned long long warp_tot[kMeshThreads / 32];
+    __shared__ unsigned long long carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += kMeshThreads) {
+        const uint32_t i = base + tid;
+        const unsigned long long v = (i < n) ? __ldcg(counts + i) : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(VX_FULL, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        unsigned long long before = carry_s + (inc - v);
+#pragma unroll
+        for (uint32_t w = 0; w < kMeshThreads / 32; ++w)
+            if (w < wid) before += warp_tot[w];
+        if (i < n) offsets[i] = before;
+        __syncthreads();
+        if (tid == kMeshThreads - 1) carry_s = before + v;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry_s;
+}
+
+// Called by every CTA of the count kernel after its count is written.
+__device__ __forceinline__ void finish_with_scan(const vx_mesh_args &a)
+{
+    __shared__ uint32_t is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // counts[m] visible before the ticket
+        const uint32_t ticket = atomicAdd(a.ticket, 1u);
+        is_last = (ticket == gridDim.x - 1u);
+        if (is_last) *a.ticket = 0;                        // re-armed for the next launch
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        scan_counts_cta(a.counts, a.offsets, a.n);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // pass 1: quads per chunk
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMeshThreads)
@@ -235,6 +354,7 @@ vx_mesh_count_kernel(const vx_mesh_args a)
     const uint32_t m = blockIdx.x;
     if (a.mesh_mask && a.mesh_mask[m] == 0) {
         if (threadIdx.x == 0) a.counts[m] = 0;
+        finish_with_scan(a);
         return;
     }
     stage_chunk<kMeshThreads>(s, a, m);
@@ -251,48 +371,7 @@ vx_mesh_count_kernel(const vx_mesh_args a)
         for (int w = 0; w < kMeshThreads / 32; ++w) tot += warp_sums[w];
         a.counts[m] = tot;
     }
-}
-
-// ---------------------------------------------------------------------------
-// exclusive scan of the counts -> uint64 offsets[n+1]   (single CTA)
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-vx_scan_kernel(const uint32_t *__restrict__ counts, uint64_t *__restrict__ offsets, uint32_t n)
-{
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ unsigned long long carry_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
-        const unsigned long long v = (i < n) ? counts[i] : 0ull;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long t = __shfl_up_sync(VX_FULL, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
-        }
-        if (lane == 31) warp_tot[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long w = warp_tot[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long t = __shfl_up_sync(VX_FULL, w, d);
-                if (lane >= (uint32_t)d) w += t;
-            }
-            warp_tot[lane] = w;       // inclusive
-        }
-        __syncthreads();
-        const unsigned long long carry = carry_s;
-        const unsigned long long before = carry + (wid ? warp_tot[wid - 1] : 0ull) + (inc - v);
-        if (i < n) offsets[i] = before;
-        __syncthreads();
-        if (tid == 1023) carry_s = before + v;
-        __syncthreads();
-    }
-    if (tid == 0) offsets[n] = carry_s;
+    finish_with_scan(a);
 }
 
 // ---------------------------------------------------------------------------
@@ -520,6 +599,24 @@ cudaError_t vx_launch_pack(const uint8_t *blocks, uint32_t n, uint32_t *occ, uin
 cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t *launches)
 {
     if (a.n == 0 || a.hi <= a.lo) return cudaSuccess;
+    if (a.n <= kSmallResolve) {
+        vx_resolve_args b = a;
+        b.table_size = 64;
+        while (b.table_size < 2 * a.n) b.table_size <<= 1;
+        const size_t smem = (size_t)b.table_size * 4 + (size_t)a.n * 12;      // <= 32 KB + 48 KB
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 64 && !configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+        }
+        vx_resolve_small_kernel<<<1, 1024, smem, s>>>(b);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaMemsetAsync(a.table, 0xff, sizeof(int32_t) * a.table_size, s);
     if (e != cudaSuccess) return e;
     if (a.halo_count) {
@@ -545,14 +642,6 @@ cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t
 {
     if (a.n == 0) return cudaSuccess;
     vx_mesh_count_kernel<<<a.n, kMeshThreads, 0, s>>>(a);
-    if (launches) ++*launches;
-    return cudaGetLastError();
-}
-
-cudaError_t vx_launch_scan(const uint32_t *counts, uint64_t *offsets, uint32_t n, cudaStream_t s,
-                           uint64_t *launches)
-{
-    vx_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, n);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

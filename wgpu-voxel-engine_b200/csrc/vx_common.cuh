@@ -52,12 +52,12 @@ struct vx_mesh_args {
     vx_instance *out;
     unsigned long long capacity;
     uint32_t *status;           // optional
+    uint32_t *ticket;           // count kernel: zero-initialised CTA ticket (last CTA runs the scan)
     uint32_t n;
     uint32_t m0;                // emit: first chunk of this launch
     unsigned long long quad_base;   // emit: offsets value that maps to out[0]
 };
 cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t *launches);
-cudaError_t vx_launch_scan(const uint32_t *counts, uint64_t *offsets, uint32_t n, cudaStream_t s, uint64_t *launches);
 cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches);
 cudaError_t vx_launch_pack(const uint8_t *blocks, uint32_t n, uint32_t *occ, uint32_t *typ,
                            uint32_t *status, cudaStream_t s, uint64_t *launches);

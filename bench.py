@@ -48,24 +48,35 @@ INSTANCE_BYTES = 68
 METRIC = "chunks/sec gen+mesh (device-timed)"
 
 
-def ring_coords(step: int, rank: int = 0) -> np.ndarray:
-    """The 32x32 ring around the player's chunk; the player walks (+5, +3) chunks per step.
-    Rank r owns the tile r*32 further along z."""
-    cx, cz = 5 * step, 3 * step + RING * rank
-    xs = np.arange(cx - RING // 2, cx + RING // 2, dtype=np.int32)
-    zs = np.arange(cz - RING // 2, cz + RING // 2, dtype=np.int32)
+def ring_coords(step: int, rank: int = 0, ring: int = RING) -> np.ndarray:
+    """The ring x ring tile around the player's chunk; the player walks (+5, +3) chunks per step.
+    Rank r owns the tile r*ring further along z (chunk-coordinate sharding)."""
+    cx, cz = 5 * step, 3 * step + ring * rank
+    xs = np.arange(cx - ring // 2, cx + ring // 2, dtype=np.int32)
+    zs = np.arange(cz - ring // 2, cz + ring // 2, dtype=np.int32)
     z, x = np.meshgrid(zs, xs, indexing="ij")
     return np.stack([x.reshape(-1), np.zeros(x.size, np.int32), z.reshape(-1)], axis=1).astype(np.int32)
 
 
-def region_masks(coords: np.ndarray, step: int, world: int) -> np.ndarray:
-    """Neighbour k present iff inside the whole 32 x 32*world region of this step."""
+def region_masks(coords: np.ndarray, step: int, world: int, ring: int = RING) -> np.ndarray:
+    """Neighbour k (-x,+x,-z,+z) present iff inside the whole ring x ring*world region of this step;
+    a present neighbour owned by another rank becomes a halo slab recomputed locally."""
     cx, cz = 5 * step, 3 * step
-    x0, x1 = cx - RING // 2, cx + RING // 2 - 1
-    z0, z1 = cz - RING // 2, cz - RING // 2 + RING * world - 1
+    x0, x1 = cx - ring // 2, cx + ring // 2 - 1
+    z0, z1 = cz - ring // 2, cz - ring // 2 + ring * world - 1
     x, z = coords[:, 0], coords[:, 2]
     m = (x - 1 >= x0) * 1 + (x + 1 <= x1) * 2 + (z - 1 >= z0) * 4 + (z + 1 <= z1) * 8
     return m.astype(np.uint8)
+
+
+def reduce_over_ranks(x: float, op: str, dist=None, device=None) -> float:
+    """max / sum of a scalar over all ranks (identity without a process group)."""
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())
 
 
 class ClockSampler:
@@ -187,18 +198,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_over_ranks(x, "max", dist, dev)
 
     def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_over_ranks(x, "sum", dist, dev)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

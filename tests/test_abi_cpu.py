@@ -81,3 +81,22 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "vox_oracle" not in text and "libvoxoracle" not in text and "import oracle" not in text \
                     and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_rust_bindings_cover_the_header():
+    # the Rust FFI crate cannot be compiled here (no rustc): keep it in lock-step with the header
+    rs = open(os.path.join(ROOT, "wgpu-voxel-engine_b200", "rust", "voxb200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (vx_[a-z0-9_]+)\s*\(", rs))
+    assert declared == set(_declared_symbols())
+
+
+def test_cpp_host_mirror_compiles(vox, tmp_path):
+    import subprocess
+    host = os.path.join(ROOT, "wgpu-voxel-engine_b200", "host")
+    exe = str(tmp_path / "host_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(host, "host_demo.cpp"),
+                           "-L" + os.path.dirname(vox.SO_PATH), "-lvoxb200",
+                           "-Wl,-rpath," + os.path.dirname(vox.SO_PATH), "-o", exe])
+    if vox._lib.lib().vx_device_count() <= 0:
+        r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stdout          # loud failure, no fallback

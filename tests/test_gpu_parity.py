@@ -318,3 +318,28 @@ def test_multi_gpu_context_equals_single(ctx, vox):
         f1 = ctx.fill(coords, noise=True)
         f2 = c2.fill(coords, noise=True)
         assert np.array_equal(f1["noise"], f2["noise"])
+
+
+def test_cpp_host_mirror_matches_oracle(vox, oracle, tmp_path):
+    """The reference's call site written against host/voxb200.hpp (C++), checked against the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "wgpu-voxel-engine_b200", "host")
+    exe = str(tmp_path / "host_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(host, "host_demo.cpp"),
+                           "-L" + os.path.dirname(vox.SO_PATH), "-lvoxb200",
+                           "-Wl,-rpath," + os.path.dirname(vox.SO_PATH), "-o", exe])
+    out = dict(line.split(None, 1) for line in subprocess.check_output([exe], text=True).splitlines())
+
+    def fnv(b, h=2166136261):
+        for v in b:
+            h = ((h ^ v) * 16777619) & 0xFFFFFFFF
+        return h
+    cubes = oracle.generate_terrain((0, 0, 0))
+    assert out["cubes_fnv"] == "%08x" % fnv(cubes.tobytes())
+    want = _canon(oracle.create_mesh((0, 0, 0), cubes, [oracle.generate_terrain((-1, 0, 0)), None, None,
+                                                       oracle.generate_terrain((0, 0, 1))]))
+    assert int(out["instances_len"]) == len(want)
+    assert out["instances_fnv"] == "%08x" % fnv(want.tobytes())
+    assert out["frustum"].split() == ["1", "0"]

@@ -1,0 +1,135 @@
+//! Drop-in replacements for the hot-path bodies of the reference's `src/chunk.rs`,
+//! `src/perlin_noise.rs` and `src/frustum_culling.rs`, forwarding to libvoxb200 through
+//! `voxb200-sys`.  Signatures are the reference's (chunk.rs:21, :48-52; frustum_culling.rs:16);
+//! see INTEGRATION.md for the three-line patch at each call site.
+//! NOT COMPILED HERE (no rustc in the build image).
+use crate::coordinate::ChunkCoord3D;
+use crate::cube::{Cube, CubeType};
+use crate::renderer::instance::InstanceRaw;
+use std::ffi::CStr;
+use std::sync::Arc;
+use voxb200_sys as ffi;
+
+/// One GPU context per process (thread-safe; calls on it are serialised by the library).
+pub struct B200 {
+    ctx: *mut ffi::vx_ctx,
+}
+unsafe impl Send for B200 {}
+unsafe impl Sync for B200 {}
+
+fn check(rc: i32) {
+    if rc != ffi::VX_OK {
+        // the reference has no error path here: it panics (chunk_builder.rs:83,107,128)
+        let msg = unsafe { CStr::from_ptr(ffi::vx_last_error()) }.to_string_lossy().into_owned();
+        panic!("voxb200 error {}: {}", rc, msg);
+    }
+}
+
+impl B200 {
+    pub fn new() -> Arc<Self> {
+        let mut ctx = std::ptr::null_mut();
+        check(unsafe { ffi::vx_create(std::ptr::null(), 0, &mut ctx) }); // 0 = every GPU of the box
+        Arc::new(Self { ctx })
+    }
+}
+impl Drop for B200 {
+    fn drop(&mut self) {
+        unsafe { ffi::vx_destroy(self.ctx) }
+    }
+}
+
+fn cube_from_id(id: u8) -> Cube {
+    Cube::new(match id {
+        0 => CubeType::GRASS,
+        1 => CubeType::DIRT,
+        _ => CubeType::AIR,
+    })
+}
+
+/// Body of `Chunk::generate_terrain` (chunk.rs:27-46): replaces the simdnoise call and the
+/// threshold loop.  `cubes` ends up in the same idx order (x + 32 z + 1024 y).
+pub fn generate_terrain(gpu: &B200, cubes: &mut Vec<Cube>, pos: ChunkCoord3D) {
+    let coords = [pos.x, pos.y, pos.z];
+    let mut ids = vec![0u8; ffi::VX_VOXELS];
+    check(unsafe {
+        ffi::vx_fill(gpu.ctx, coords.as_ptr(), 1, std::ptr::null(), ids.as_mut_ptr(),
+                     std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut())
+    });
+    cubes.extend(ids.into_iter().map(cube_from_id));
+}
+
+/// Body of `Chunk::create_mesh` up to the wgpu upload (chunk.rs:48-57, 254-260): returns the
+/// `Vec<InstanceRaw>` that `ChunkMesh::new` hands to `create_buffer_init`.
+/// `own` / `adjacent` are the CubeType bytes of the chunk and of its -x,+x,-z,+z neighbours.
+pub fn create_mesh_instances(gpu: &B200, pos: ChunkCoord3D, own: &[u8],
+                             adjacent: [Option<(ChunkCoord3D, &[u8])>; 4]) -> Vec<InstanceRaw> {
+    let mut coords = vec![pos.x, pos.y, pos.z];
+    let mut blocks = own.to_vec();
+    let mut nbr = [-1i32; 4];
+    for (k, a) in adjacent.iter().enumerate() {
+        if let Some((p, b)) = a {
+            nbr[k] = (coords.len() / 3) as i32;
+            coords.extend_from_slice(&[p.x, p.y, p.z]);
+            blocks.extend_from_slice(b);
+        }
+    }
+    let n = coords.len() / 3;
+    let mut nbr_idx = vec![-1i32; n * 4];
+    nbr_idx[..4].copy_from_slice(&nbr);
+    let mut mesh_mask = vec![0u8; n];
+    mesh_mask[0] = 1;
+    let (mut counts, mut offsets, mut total) = (vec![0u32; n], vec![0u64; n + 1], 0u64);
+    let mut inst: Vec<InstanceRaw> = Vec::with_capacity(ffi::VX_MAX_QUADS_PER_CHUNK);
+    check(unsafe {
+        ffi::vx_mesh(gpu.ctx, coords.as_ptr(), n, blocks.as_ptr(), nbr_idx.as_ptr(), mesh_mask.as_ptr(),
+                     counts.as_mut_ptr(), offsets.as_mut_ptr(), inst.as_mut_ptr() as *mut ffi::vx_instance,
+                     ffi::VX_MAX_QUADS_PER_CHUNK, &mut total)
+    });
+    unsafe { inst.set_len(total as usize) }; // InstanceRaw and vx_instance share one repr(C) layout
+    inst
+}
+
+/// The fast path: the worker closure of chunk_builder.rs:80-84 for a whole coordinate list in
+/// one call (noise + meshing on the GPU, instances back through pinned double-buffered D2H).
+/// Returns per-chunk (cube ids, instances).  `nbr_mask[i]` bit k = neighbour k counts as loaded.
+pub fn build_chunks(gpu: &B200, positions: &[ChunkCoord3D], nbr_mask: Option<&[u8]>)
+                    -> Vec<(Vec<u8>, Vec<InstanceRaw>)> {
+    let n = positions.len();
+    let coords: Vec<i32> = positions.iter().flat_map(|p| vec![p.x, p.y, p.z]).collect();
+    let mask_ptr = nbr_mask.map_or(std::ptr::null(), |m| m.as_ptr());
+    let (mut counts, mut offsets, mut total) = (vec![0u32; n], vec![0u64; n + 1], 0u64);
+    check(unsafe {
+        ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
+                         offsets.as_mut_ptr(), std::ptr::null_mut(), 0, &mut total, std::ptr::null_mut())
+    });
+    let mut inst: Vec<InstanceRaw> = Vec::with_capacity(total as usize);
+    let mut blocks = vec![0u8; n * ffi::VX_VOXELS];
+    check(unsafe {
+        ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
+                         offsets.as_mut_ptr(), inst.as_mut_ptr() as *mut ffi::vx_instance, total as usize,
+                         &mut total, blocks.as_mut_ptr())
+    });
+    unsafe { inst.set_len(total as usize) };
+    (0..n).map(|i| {
+        (blocks[i * ffi::VX_VOXELS..(i + 1) * ffi::VX_VOXELS].to_vec(),
+         inst[offsets[i] as usize..offsets[i + 1] as usize].to_vec())
+    }).collect()
+}
+
+/// `Frustum::matrix_to_planes` (frustum_culling.rs:47-85): `m` = `matrix.data.0` flattened.
+pub fn matrix_to_planes(m: &[f32; 16]) -> [f32; 24] {
+    let mut planes = [0f32; 24];
+    check(unsafe { ffi::vx_planes_from_matrix(m.as_ptr(), planes.as_mut_ptr()) });
+    planes
+}
+
+/// `Frustum::contains` (frustum_culling.rs:16-40) for a whole list in one launch; use it at
+/// chunk_builder.rs:217-255 (enqueue gate) and world.rs:34-37 (draw gate).
+pub fn frustum_contains_many(gpu: &B200, planes: &[f32; 24], positions: &[ChunkCoord3D]) -> Vec<bool> {
+    let coords: Vec<i32> = positions.iter().flat_map(|p| vec![p.x, p.y, p.z]).collect();
+    let mut vis = vec![0u8; positions.len()];
+    check(unsafe {
+        ffi::vx_frustum_cull(gpu.ctx, planes.as_ptr(), 1, coords.as_ptr(), positions.len(), vis.as_mut_ptr())
+    });
+    vis.into_iter().map(|v| v != 0).collect()
+}

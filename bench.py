@@ -140,7 +140,7 @@ def run_reference(args, rank: int):
     cpu_work_function(range(args.warmup), cores) if args.warmup else None
     dt, quads = cpu_work_function(range(args.warmup, args.warmup + args.steps), cores)
     v = CHUNKS_PER_STEP * args.steps / dt
-    print(json.dumps({
+    emit_json(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "chunks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -336,12 +336,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "cpu_baseline": cpu,
         "near_threshold_voxels": {"abs_noise_le_1e-6": census, "of": n * VOXELS},
     }
-    print(json.dumps(line))
+    emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(obj) -> None:
+    """Exactly one JSON line on the real stdout (library chatter such as NCCL's version banner
+    goes to stderr: fd 1 is pointed at fd 2 for the duration of the run)."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -18,6 +18,7 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
     L = C.CDLL(so)
     L.shim_noise_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    L.shim_noise_chunk_sign.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     return L
 
 
@@ -36,3 +37,19 @@ def test_device_noise_other_params(shim, oracle):
     shim.shim_noise_chunk(c.ctypes.data, 12345, 0.9, 1.7, 0.4, 5, out.ctypes.data)
     want = oracle.noise_chunk((3, -1, 4), oracle.default_params(seed=12345, freq=0.9, gain=1.7, lacunarity=0.4, octaves=5))
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("coord,seed,gain,lac,freq", [((0, 0, 0), 1, 2.5, 0.5, 0.09), ((-1, 0, -1), 1, 2.5, 0.5, 0.09),
+                                                       ((511, 0, -512), 1, 2.5, 0.5, 0.09), ((9, -3, 4), 77, -3.0, 0.7, 0.2),
+                                                       ((100000, 3, -99999), 5, 1.0, 2.0, 0.03)])
+def test_sign_only_gradient_variant(shim, oracle, coord, seed, gain, lac, freq):
+    """vxn_simplex3_sign (coefficient-table gradient on the FMA pipe) equals the exact noise in value;
+    only the sign of a zero may differ, which `noise < 0` cannot see."""
+    c = np.array(coord, np.int32)
+    out = np.empty(32768, np.float32)
+    shim.shim_noise_chunk_sign(c.ctypes.data, seed, freq, gain, lac, out.ctypes.data)
+    want = oracle.noise_chunk(coord, oracle.default_params(seed=seed, freq=freq, gain=gain, lacunarity=lac))
+    assert np.array_equal(out, want)                       # value equality (+0 == -0)
+    nz = want != 0
+    assert np.array_equal(out.view(np.uint32)[nz], want.view(np.uint32)[nz])
+    assert np.array_equal(out < 0, want < 0)

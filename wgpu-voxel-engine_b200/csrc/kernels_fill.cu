@@ -157,7 +157,16 @@ __global__ void __launch_bounds__(256)
 vx_fill_brick_kernel(const vx_fill_args a)
 {
     __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
+    // gradient coefficient table (2 KB, one column per lane & 7) placed on a 2048-byte boundary
+    // of the shared window inside a 4 KB buffer
+    __shared__ __align__(16) float4 s_lut_raw[2 * VXN_LUT_FLOAT4S];
+    const uint32_t lut_raw = (uint32_t)__cvta_generic_to_shared(s_lut_raw);
+    const uint32_t lut_base = (lut_raw + 2047u) & ~2047u;
+    float4 *s_lut = s_lut_raw + ((lut_base - lut_raw) >> 4);
+    if (threadIdx.x < VXN_LUT_FLOAT4S) s_lut[threadIdx.x] = vxn_grad_coeffs(threadIdx.x >> 3);
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
+    const vxn_lut_ref lut_lane = lut_base + (lane & 7u) * 16u;
     const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
     const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
     const float ox = (float)(int32_t)((uint32_t)cx * 32u);
@@ -188,17 +197,17 @@ vx_fill_brick_kernel(const vx_fill_args a)
         const float z0 = __fmul_rn(__fadd_rn(oz, (float)y), freq);
         const float z1 = __fmul_rn(z0, lac);
         const float z2 = __fmul_rn(z1, lac);
-        const float u = __fmul_rn(vxn_simplex3(hx[2], hy[2], z2, hxy[2], seed), amp2);
+        const float u = __fmul_rn(vxn_simplex3_sign(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
         bool solid;
         if (__all_sync(VX_FULL, fabsf(u) > thr2)) {
             solid = u < 0.0f;
         } else {
-            const float t = __fmul_rn(vxn_simplex3(hx[1], hy[1], z1, hxy[1], seed), amp1);
+            const float t = __fmul_rn(vxn_simplex3_sign(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1);
             const float ut = __fadd_rn(u, t);
             if (__all_sync(VX_FULL, fabsf(ut) > thr1)) {
                 solid = ut < 0.0f;
             } else {
-                const float s1 = vxn_simplex3(hx[0], hy[0], z0, hxy[0], seed);
+                const float s1 = vxn_simplex3_sign(hx[0], hy[0], z0, hxy[0], seed, lut_lane);
                 // reference association: r = s1; r = t + r; r = u + r
                 solid = __fadd_rn(u, __fadd_rn(t, s1)) < 0.0f;
             }
@@ -268,7 +277,11 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
     if (a.max_units == 0) return cudaSuccess;
     if (launches) ++*launches;
     // octaves = 3 (perlin_noise.rs:18) without noise/census output: sign-only brick kernel
-    if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && !a.force_exact) {
+    // (the coefficient-table gradient multiplies by 0, so coordinates must stay finite:
+    //  |world * freq * lac^k| <= 2^31 * |freq| * max(1, lac^2) must not overflow f32)
+    const float reach = 2147483648.0f * fabsf(a.p.freq) * fmaxf(1.0f, a.p.lacunarity * a.p.lacunarity);
+    const bool tame = isfinite(reach) && reach < 1e30f && isfinite(a.p.gain);
+    if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && !a.force_exact && tame) {
         vx_fill_args b = a;
         // |simplex_3d| <= 0.030585; 0.0306 plus a relative slack far above the f32 rounding of u, t, u+t
         const float g1 = fabsf(a.p.gain), g2 = fabsf(a.p.gain * a.p.gain);

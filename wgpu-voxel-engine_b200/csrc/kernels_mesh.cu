@@ -406,6 +406,10 @@ constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
 constexpr int kLutStride = 20;               // words per LUT row (80 B: 16-B aligned, bank-spread)
 constexpr int kTileWords = 32 * 17 + 4;      // one warp tile (32 instances) + alignment lead
+#ifndef VX_STAGE_BUFS
+#define VX_STAGE_BUFS 2
+#endif
+constexpr int kStageBufs = VX_STAGE_BUFS;   // staging tiles per warp
 
 struct EmitSmem {
     ChunkSmem c;
@@ -413,7 +417,7 @@ struct EmitSmem {
     __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
     uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
     uint32_t warp_tot[kEmitWarps];
-    __align__(16) uint32_t stage[kEmitWarps][2][kTileWords];   // per-warp double-buffered tiles
+    __align__(16) uint32_t stage[kEmitWarps][kStageBufs][kTileWords];   // per-warp staging tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -509,9 +513,9 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     uint32_t it = 0;
 
     for (uint32_t tile = wid; tile < n_tiles; tile += kEmitWarps, ++it) {
-        uint32_t *stg = s.stage[wid][it & 1u];
+        uint32_t *stg = s.stage[wid][it % kStageBufs];
         // the bulk store that last read this buffer (two tiles ago) must be done reading it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kStageBufs - 1) : "memory");
         __syncwarp();
 
         const uint32_t q0 = tile << 5;

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck).
+  compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import voxb200  # noqa: E402
+
+ctx = voxb200.Context()
+coords = np.array([(x, 0, z) for z in range(-2, 2) for x in range(-2, 2)], np.int32)
+r = ctx.gen_mesh(coords, blocks=True)                                   # resolve, brick fill, count+scan, emit
+m = np.full(len(coords), 15, np.uint8)
+r2 = ctx.gen_mesh(coords[:5], nbr_mask=m[:5])                           # halo fill
+f = ctx.fill(coords[:3], noise=True, census=True, occupancy=True)       # exact fill
+f4 = ctx.fill(coords[:2], params=voxb200.default_noise_params(octaves=4))   # generic octave loop
+g = np.indices((32, 32, 32)).sum(axis=0) & 1
+cb = np.where(g == 0, 0, 2).astype(np.uint8).reshape(-1)
+mm = ctx.mesh(coords[:2], np.stack([cb, r.blocks[0]]))                   # pack, count, emit (98304 quads)
+planes = np.random.default_rng(0).standard_normal((70, 6, 4)).astype(np.float32)
+v = ctx.frustum_cull(planes, coords)
+b = ctx.frustum_cull(planes, coords, bits=True)
+print("ok", r.total, r2.total, f["near_zero"], mm.total, int(v.sum()), ctx.launch_count)

@@ -42,8 +42,13 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
     const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
 
     for (uint32_t f = 0; f < nf; ++f) {
-        bool in0 = live, in1 = live, in2 = live, in3 = live, in4 = live, in5 = live, in6 = live, in7 = live;
-#pragma unroll 1
+        // Per corner, the minimum over the planes of its distance: the corner is inside all six
+        // planes iff that minimum is not < 0.  fminf ignores a NaN operand, which is the
+        // reference's behaviour (a NaN distance never rejects, frustum_culling.rs:33).
+        const float inf = __int_as_float(0x7f800000);
+        float m0 = inf, m1 = inf, m2 = inf, m3 = inf, m4 = inf, m5 = inf, m6 = inf, m7 = inf;
+        bool dead = false;
+#pragma unroll
         for (uint32_t p = 0; p < 6; ++p) {
             const float4 pl = s_pl[f * 6 + p];
             const float ax0 = __fmul_rn(pl.x, x0), ax1 = __fmul_rn(pl.x, x1);
@@ -51,18 +56,26 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
             const float cz0 = __fmul_rn(pl.z, z0), cz1 = __fmul_rn(pl.z, z1);
             const float s00 = __fadd_rn(ax0, by0), s10 = __fadd_rn(ax1, by0);
             const float s01 = __fadd_rn(ax0, by1), s11 = __fadd_rn(ax1, by1);
-            in0 = in0 && !(__fadd_rn(__fadd_rn(s00, cz0), pl.w) < 0.0f);
-            in1 = in1 && !(__fadd_rn(__fadd_rn(s10, cz0), pl.w) < 0.0f);
-            in2 = in2 && !(__fadd_rn(__fadd_rn(s00, cz1), pl.w) < 0.0f);
-            in3 = in3 && !(__fadd_rn(__fadd_rn(s10, cz1), pl.w) < 0.0f);
-            in4 = in4 && !(__fadd_rn(__fadd_rn(s01, cz0), pl.w) < 0.0f);
-            in5 = in5 && !(__fadd_rn(__fadd_rn(s11, cz0), pl.w) < 0.0f);
-            in6 = in6 && !(__fadd_rn(__fadd_rn(s01, cz1), pl.w) < 0.0f);
-            in7 = in7 && !(__fadd_rn(__fadd_rn(s11, cz1), pl.w) < 0.0f);
-            const bool any = in0 || in1 || in2 || in3 || in4 || in5 || in6 || in7;
-            if (!__any_sync(VX_FULL, any)) break;
+            m0 = fminf(m0, __fadd_rn(__fadd_rn(s00, cz0), pl.w));
+            m1 = fminf(m1, __fadd_rn(__fadd_rn(s10, cz0), pl.w));
+            m2 = fminf(m2, __fadd_rn(__fadd_rn(s00, cz1), pl.w));
+            m3 = fminf(m3, __fadd_rn(__fadd_rn(s10, cz1), pl.w));
+            m4 = fminf(m4, __fadd_rn(__fadd_rn(s01, cz0), pl.w));
+            m5 = fminf(m5, __fadd_rn(__fadd_rn(s11, cz0), pl.w));
+            m6 = fminf(m6, __fadd_rn(__fadd_rn(s01, cz1), pl.w));
+            m7 = fminf(m7, __fadd_rn(__fadd_rn(s11, cz1), pl.w));
+            if (p == 1 || p == 3) {
+                // the result is a pure function, so the remaining planes can be skipped once no
+                // lane of the warp has a live corner
+                const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+                if (!__any_sync(VX_FULL, live && !(best < 0.0f))) {
+                    dead = true;
+                    break;
+                }
+            }
         }
-        const bool vis = in0 || in1 || in2 || in3 || in4 || in5 || in6 || in7;
+        const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+        const bool vis = live && !dead && !(best < 0.0f);
         const uint32_t word = __ballot_sync(VX_FULL, vis);
         if (WANT_BYTES && live) visible[(size_t)(f0 + f) * n + i] = vis ? 1 : 0;
         if (WANT_BITS && (threadIdx.x & 31) == 0 && live) bits[(size_t)(f0 + f) * n_words + (i >> 5)] = word;

@@ -404,6 +404,10 @@ __constant__ uint32_t c_tex[2][6] = {
 
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
+#ifndef VX_EMIT_SPLIT
+#define VX_EMIT_SPLIT 1
+#endif
+constexpr int kEmitSplit = VX_EMIT_SPLIT;   // CTAs per chunk
 constexpr int kLutStride = 20;               // words per LUT row (80 B: 16-B aligned, bank-spread)
 constexpr int kTileWords = 32 * 17 + 4;      // one warp tile (32 instances) + alignment lead
 #ifndef VX_STAGE_BUFS
@@ -413,7 +417,8 @@ constexpr int kStageBufs = VX_STAGE_BUFS;   // staging tiles per warp
 
 struct EmitSmem {
     ChunkSmem c;
-    uint32_t rowbase[VX_ROWS + 1];           // exclusive scan of the per-row quad counts
+    uint32_t nz_base[VX_ROWS + 1];           // first quad of each NON-EMPTY row (+ sentinel = count)
+    uint16_t nz_row[VX_ROWS];                // its row index
     __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
     uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
     uint32_t warp_tot[kEmitWarps];
@@ -446,11 +451,13 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitSmem &s = *reinterpret_cast<EmitSmem *>(smem_raw);
-    const uint32_t m = a.m0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    // kEmitSplit CTAs share one chunk (interleaved tiles): more, shorter CTAs -> smaller tail
+    const uint32_t part = blockIdx.x % kEmitSplit, n_chunks = gridDim.x / kEmitSplit;
+    const uint32_t m = a.m0 + blockIdx.x / kEmitSplit, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
-    // this launch covers chunks [m0, m0 + gridDim.x); its quads land at
+    // this launch covers chunks [m0, m0 + n_chunks); its quads land at
     // out[offsets[m] - quad_base]
-    const unsigned long long launch_quads = a.offsets[a.m0 + gridDim.x] - a.quad_base;
+    const unsigned long long launch_quads = a.offsets[a.m0 + n_chunks] - a.quad_base;
     if (launch_quads > a.capacity) {
         if (blockIdx.x == 0 && tid == 0 && a.status) atomicOr(a.status, VX_ST_OVERFLOW);
         return;
@@ -476,13 +483,15 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     }
     stage_chunk<kEmitThreads>(s.c, a, m);        // ends with __syncthreads()
 
-    // ---- per-row quad counts -> exclusive scan in row order ---------------------------
+    // ---- per-row quad counts -> exclusive scan in row order, compacted to the non-empty rows
+    //      (one packed scan: quads in bits 0-19, non-empty rows in bits 20-30) ------------------
+    uint32_t nzc;
     {
         uint32_t cnt[4], mine = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
             cnt[j] = row_count(row_faces(s.c, tid * 4 + j));
-            mine += cnt[j];
+            mine += cnt[j] + (cnt[j] ? (1u << 20) : 0u);
         }
         uint32_t inc = mine;
 #pragma unroll
@@ -492,16 +501,22 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         }
         if (lane == 31) s.warp_tot[wid] = inc;
         __syncthreads();
-        uint32_t base = inc - mine;
+        uint32_t base = inc - mine, total = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < (uint32_t)kEmitWarps; ++w)
+        for (uint32_t w = 0; w < (uint32_t)kEmitWarps; ++w) {
             if (w < wid) base += s.warp_tot[w];
+            total += s.warp_tot[w];
+        }
+        nzc = total >> 20;
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
-            s.rowbase[tid * 4 + j] = base;
-            base += cnt[j];
+            if (cnt[j]) {
+                s.nz_base[base >> 20] = base & 0xfffffu;
+                s.nz_row[base >> 20] = (uint16_t)(tid * 4 + j);
+                base += cnt[j] + (1u << 20);
+            }
         }
-        if (tid == kEmitThreads - 1) s.rowbase[VX_ROWS] = base;
+        if (tid == 0) s.nz_base[nzc] = count;
         __syncthreads();                         // last CTA-wide barrier
     }
 
@@ -512,7 +527,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     const uint32_t n_tiles = (count + 31u) >> 5;
     uint32_t it = 0;
 
-    for (uint32_t tile = wid; tile < n_tiles; tile += kEmitWarps, ++it) {
+    for (uint32_t tile = wid + part * kEmitWarps; tile < n_tiles; tile += kEmitWarps * kEmitSplit, ++it) {
         uint32_t *stg = s.stage[wid][it % kStageBufs];
         // the bulk store that last read this buffer (two tiles ago) must be done reading it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kStageBufs - 1) : "memory");
@@ -522,14 +537,19 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         const uint32_t nq = min(32u, count - q0);
         const unsigned long long G = chunk_word0 + (unsigned long long)q0 * 17ull;
         const uint32_t lead = (uint32_t)(G & 3ull);            // stage word i <-> global word G - lead + i
+        // Row of every quad of the tile, cooperatively: idx0 = the non-empty row holding q0 (two
+        // 32-way ballots over nz_base), then each later row start inside the tile sets one bit.
+        const uint32_t c_probe = s.nz_base[min(lane * 32u, nzc)];
+        const uint32_t cblk = __popc(__ballot_sync(VX_FULL, lane * 32u < nzc && c_probe <= q0)) - 1u;
+        const uint32_t f_probe = s.nz_base[min(cblk * 32u + lane, nzc)];
+        const uint32_t idx0 = cblk * 32u + __popc(__ballot_sync(VX_FULL, cblk * 32u + lane < nzc && f_probe <= q0)) - 1u;
+        const uint32_t nxt = s.nz_base[min(idx0 + 1u + lane, nzc)] - q0;       // >= 1
+        const uint32_t starts = __reduce_or_sync(VX_FULL, (idx0 + 1u + lane < nzc && nxt < 32u) ? (1u << nxt) : 0u);
         if (lane < nq) {
             const uint32_t q = q0 + lane;
-            // row: largest r with rowbase[r] <= q (empty rows tie; the last one is the owner)
-            uint32_t r = 0;
-#pragma unroll
-            for (uint32_t step = 512; step > 0; step >>= 1)
-                if (s.rowbase[r + step] <= q) r += step;
-            uint32_t k = q - s.rowbase[r];
+            const uint32_t idx = idx0 + __popc(starts & ((2u << lane) - 1u));
+            const uint32_t r = s.nz_row[idx];
+            uint32_t k = q - s.nz_base[idx];
             const RowFaces f = row_faces(s.c, r);
             // 3-bit vertical counters: per x, c(x) = number of faces = s0 + 2 s1 + 4 s2
             const uint32_t a0 = f.m[0] ^ f.m[1] ^ f.m[2], a1 = (f.m[0] & f.m[1]) | (f.m[2] & (f.m[0] ^ f.m[1]));
@@ -577,9 +597,15 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         if (lane == 0 && Gb > Ga)
             bulk_store(out32 + Ga, stg + (uint32_t)(Ga - G) + lead, (uint32_t)(Gb - Ga) * 4u);
         const uint32_t head = (uint32_t)(Ga - G), tail0 = (uint32_t)(Gb - G);
-        for (uint32_t i = lane; i < head + (nwords - tail0); i += 32u) {
-            const uint32_t wi = (i < head) ? i : tail0 + (i - head);
-            out32[G + wi] = stg[lead + wi];
+        if (Gb > Ga) {
+            // at most 3 head + 3 tail words: one predicated store
+            const uint32_t n_edge = head + (nwords - tail0);
+            if (lane < n_edge) {
+                const uint32_t wi = (lane < head) ? lane : tail0 + (lane - head);
+                out32[G + wi] = stg[lead + wi];
+            }
+        } else {
+            for (uint32_t i = lane; i < nwords; i += 32u) out32[G + i] = stg[lead + i];
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
@@ -663,7 +689,7 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    vx_mesh_emit_kernel<<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+    vx_mesh_emit_kernel<<<len * kEmitSplit, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -251,6 +251,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * n * K / e2e_s
+    # ---- extra: the same call with 4-byte packed quads on the wire (extension, not the headline) ---
+    e2e_packed = None
+    if hasattr(ctx, "gen_mesh_packed"):
+        pq = pinned.view(np.uint32)
+        for i in range(min(W, 3)):
+            ctx.gen_mesh_packed(h_coords[i], nbr_mask=h_masks[i] if h_masks else None, out=pq)
+        barrier()
+        t0 = time.perf_counter()
+        pk_quads = 0
+        for i in range(W, W + K):
+            pk_quads += ctx.gen_mesh_packed(h_coords[i], nbr_mask=h_masks[i] if h_masks else None, out=pq).total
+        torch.cuda.synchronize()
+        pk_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_packed = {"value": world * n * K / pk_s, "unit": "chunks/s",
+                      "d2h_bytes_per_step": int(4 * n + 8 * (n + 1) + 4 * pk_quads / K),
+                      "api": "vx_gen_mesh_packed: 4-byte quad records, expanded by the renderer's vertex shader; "
+                             "NOT the reference's 68-byte wire format (SURVEY 8f rank 2 extension)"}
     t_load1 = time.time()
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
 
@@ -312,6 +330,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": 12 * n + (n if h_masks else 0),
                 "d2h_bytes_per_step": int(4 * n + 8 * (n + 1) + INSTANCE_BYTES * e2e_quads / K),
                 "api": "vx_gen_mesh (host buffers, pinned instance buffer)"},
+        "e2e_packed_extension": e2e_packed,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {

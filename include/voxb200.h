@@ -131,6 +131,22 @@ int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_par
                 vx_instance *instances, size_t capacity, uint64_t *total_out,
                 uint8_t *blocks_out);
 
+/* ---- extension: packed quads -------------------------------
+ * NOT the reference's wire format.  Same as vx_gen_mesh, but each quad is one
+ * 32-bit record instead of a 68-byte InstanceRaw, for renderers that expand in
+ * the vertex shader (17x less PCIe traffic):
+ *   bits 0-4 x | 5-9 z | 10-14 y (voxel idx inside the chunk) | 15-17 face
+ *   (VX_LEFT..VX_UP) | 18 block type (0 GRASS, 1 DIRT).
+ * Quads of chunk i are quads[offsets[i] .. offsets[i+1]), in the same order as
+ * the instances; InstanceRaw = translate(chunk*32 + (x,y,z)) * rotation(face),
+ * texture = TEXTURE_INDEX_LIST[type][slot(face)]. */
+int vx_gen_mesh_packed(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                       const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets,
+                       uint32_t *quads, size_t capacity, uint64_t *total_out);
+int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                              const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets,
+                              uint32_t *quads, size_t capacity, uint32_t *status, void *stream);
+
 /* ---- frustum -------------------------------------------------------------
  * vx_planes_from_matrix replaces Frustum::matrix_to_planes
  * (frustum_culling.rs:47-85): m = column-major Matrix4<f32> (m[c*4+r]),

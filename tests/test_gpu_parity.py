@@ -343,3 +343,27 @@ def test_cpp_host_mirror_matches_oracle(vox, oracle, tmp_path):
     assert int(out["instances_len"]) == len(want)
     assert out["instances_fnv"] == "%08x" % fnv(want.tobytes())
     assert out["frustum"].split() == ["1", "0"]
+
+
+def test_packed_quads_expand_to_the_instance_stream(ctx, oracle):
+    """Extension: 4-byte quad records carry the same quads in the same order."""
+    coords = _grid(-2, -2, 4, 4, y=1)
+    masks = np.random.default_rng(9).integers(0, 16, size=len(coords)).astype(np.uint8)
+    full = ctx.gen_mesh(coords, nbr_mask=masks)
+    pk = ctx.gen_mesh_packed(coords, nbr_mask=masks)
+    assert np.array_equal(pk.counts, full.counts) and np.array_equal(pk.offsets, full.offsets)
+    d = pk.instances.astype(np.int64)
+    chunk = np.repeat(np.arange(len(coords)), full.counts.astype(np.int64))
+    x, z, y, face, typ = d & 31, (d >> 5) & 31, (d >> 10) & 31, (d >> 15) & 7, (d >> 18) & 1
+    assert face.max() <= 5 and typ.max() == 0
+    want = np.zeros(len(d), dtype=full.instances.dtype)
+    rot = np.stack([oracle.face_rotation(f) for f in range(6)]) + np.float32(0)       # [face][row][col]
+    want["t_matrix"][:, :3, :3] = np.transpose(rot[face], (0, 2, 1))                  # t_matrix[c][r]
+    world = coords[chunk].astype(np.int64) * 32
+    want["t_matrix"][:, 3, 0] = world[:, 0] + x
+    want["t_matrix"][:, 3, 1] = world[:, 1] + y
+    want["t_matrix"][:, 3, 2] = world[:, 2] + z
+    want["t_matrix"][:, 3, 3] = 1.0
+    tex = np.array([[0, 0, 0, 0, 1, 2], [1, 1, 1, 1, 1, 1]], np.uint32)             # [type][face]: slots 0,1,2,3,5,4
+    want["texture_index"] = tex[typ, face]
+    assert _canon(full.instances).tobytes() == want.tobytes()

@@ -63,6 +63,8 @@ SIGNATURES = {
     "vx_fill": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp]),
     "vx_mesh": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vx_gen_mesh": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "vx_gen_mesh_packed": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vx_gen_mesh_packed_device": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vx_planes_from_matrix": (_i, [_vp, _vp]),
     "vx_frustum_cull": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "vx_frustum_cull_bits": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),

@@ -178,6 +178,28 @@ class Context:
         res.blocks = b
         return res
 
+    def gen_mesh_packed(self, coords, params: Optional[NoiseParams] = None, nbr_mask=None,
+                        out: Optional[np.ndarray] = None) -> MeshBatch:
+        """Extension (not the reference wire format): one uint32 record per quad, see include/voxb200.h."""
+        coords = _coords(coords)
+        n = coords.shape[0]
+        nm = None if nbr_mask is None else np.ascontiguousarray(nbr_mask, dtype=np.uint8).reshape(n)
+        counts = np.zeros(n, np.uint32)
+        offsets = np.zeros(n + 1, np.uint64)
+        total = C.c_uint64(0)
+        quads = out.view(np.uint32).reshape(-1) if out is not None else np.empty(max(1024, n * 8192), np.uint32)
+
+        def call(q):
+            return self._L.vx_gen_mesh_packed(self._h, _ptr(coords), n, C.byref(params) if params else None, _ptr(nm),
+                                              _ptr(counts), _ptr(offsets), _ptr(q), q.shape[0], C.addressof(total))
+        rc = call(quads)
+        if rc == _lib.VX_ERR_CAPACITY and out is None:
+            quads = np.empty(int(total.value), np.uint32)
+            rc = call(quads)
+        check(rc)
+        t = int(total.value)
+        return MeshBatch(counts, offsets, quads[:t], t)
+
     def _run_mesh(self, call, n, instances, capacity, out) -> MeshBatch:
         counts = np.zeros(n, np.uint32)
         offsets = np.zeros(n + 1, np.uint64)

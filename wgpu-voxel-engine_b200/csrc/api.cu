@@ -75,7 +75,6 @@ struct DevBuf {
 };
 
 constexpr size_t kArenaBytes = size_t(256) << 20;                      // per instance arena
-constexpr size_t kArenaQuads = kArenaBytes / sizeof(vx_instance);      // >= 98304 (one chunk always fits)
 constexpr size_t kSliceBytes = size_t(256) << 20;                      // staging for fill / frustum outputs
 
 struct Dev {
@@ -245,8 +244,13 @@ vx_mesh_args emit_args(const Dev &d, const int32_t *d_coords, const uint32_t *ty
 
 // Stream the instances of chunks [0, n) (device-local numbering, host copy of
 // the local offsets in h_off) to host memory through the two arenas.
-int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t n, vx_instance *h_out)
+int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t n, void *h_out_v,
+                         bool packed = false)
 {
+    const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
+    const size_t kArenaQuads = kArenaBytes / rec;
+    unsigned char *h_out = static_cast<unsigned char *>(h_out_v);
+    m.packed = packed ? 1 : 0;
     CK(d.inst[0].ensure(kArenaBytes));
     if (h_off[n] > kArenaQuads) CK(d.inst[1].ensure(kArenaBytes));
     uint32_t a = 0;
@@ -266,8 +270,7 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
             TIMED(d, d.stream, VX_K_EMIT, vx_launch_mesh_emit(m, b - a, d.stream, &d.launches));
             CK(cudaEventRecord(d.emit_done[buf], d.stream));
             CK(cudaStreamWaitEvent(d.copy, d.emit_done[buf], 0));
-            CK(cudaMemcpyAsync(h_out + h_off[a], d.inst[buf].p, q * sizeof(vx_instance), cudaMemcpyDeviceToHost,
-                               d.copy));
+            CK(cudaMemcpyAsync(h_out + h_off[a] * rec, d.inst[buf].p, q * rec, cudaMemcpyDeviceToHost, d.copy));
             CK(cudaEventRecord(d.d2h_done[buf], d.copy));
             ++k;
         }
@@ -629,9 +632,9 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
 // ---------------------------------------------------------------------------
 // fused generate + mesh
 // ---------------------------------------------------------------------------
-int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
-                       const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
-                       size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream)
+static int gen_mesh_device_impl(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                                const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, void *instances,
+                                size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream, bool packed)
 {
     if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
     if (!offsets || (n && (!coords || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
@@ -651,7 +654,8 @@ int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_no
     RET(dev_gen_count(d, s, coords, nn, 0, nn, p, nbr_mask, counts, offsets, blocks_out));
     if (instances) {
         vx_mesh_args m = emit_args(d, coords, nullptr, nullptr, counts, offsets, nn);
-        m.out = instances;
+        m.out = static_cast<vx_instance *>(instances);
+        m.packed = packed ? 1 : 0;
         m.capacity = capacity;
         m.status = status;
         TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
@@ -659,10 +663,28 @@ int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_no
     return VX_OK;
 }
 
-int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
-                const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
-                size_t capacity, uint64_t *total_out, uint8_t *blocks_out)
+int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                       const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                       size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream)
 {
+    return gen_mesh_device_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, status,
+                                blocks_out, stream, false);
+}
+
+int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                              const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, uint32_t *quads,
+                              size_t capacity, uint32_t *status, void *stream)
+{
+    return gen_mesh_device_impl(ctx, coords, n, params, nbr_mask, counts, offsets, quads, capacity, status, nullptr,
+                                stream, true);
+}
+
+static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                              const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, void *instances_v,
+                              size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
+{
+    unsigned char *instances = static_cast<unsigned char *>(instances_v);
+    const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
     if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
     if (total_out) *total_out = 0;
     if (!offsets || (n && (!coords || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
@@ -732,10 +754,26 @@ int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_par
         CK(cudaSetDevice(d.id));
         vx_mesh_args m = emit_args(d, d.coords.as<int32_t>() + 3 * (size_t)lo[di], nullptr, nullptr,
                                    d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), c);
-        RET(dev_stream_instances(d, m, loc[di].data(), c, instances + base[di]));
+        RET(dev_stream_instances(d, m, loc[di].data(), c, instances + base[di] * rec, packed));
     }
     for (Dev &d : ctx->devs) RET(sync_dev(d));
     return VX_OK;
+}
+
+int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                size_t capacity, uint64_t *total_out, uint8_t *blocks_out)
+{
+    return gen_mesh_host_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, total_out,
+                              blocks_out, false);
+}
+
+int vx_gen_mesh_packed(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                       const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, uint32_t *quads,
+                       size_t capacity, uint64_t *total_out)
+{
+    return gen_mesh_host_impl(ctx, coords, n, params, nbr_mask, counts, offsets, quads, capacity, total_out, nullptr,
+                              true);
 }
 
 // ---------------------------------------------------------------------------

@@ -15,6 +15,8 @@
 // (y,z,x) order, faces LEFT,RIGHT,BACK,FRONT,DOWN,UP -- an exclusive scan of
 // per-row counts keeps that order, so parity is a plain compare.
 // The emit kernel is HBM-write bound (68 B per quad).
+#include <cstddef>
+
 #include "vx_common.cuh"
 
 namespace {
@@ -446,6 +448,11 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 //   face  = k-th set face bit of that cube,
 // builds the 68-byte InstanceRaw in the warp's staging tile (stride-17 words,
 // bank-conflict free) and the tile leaves through one TMA bulk store.
+//
+// PACKED = true writes one 32-bit quad record instead of the 68-byte instance (extension for
+// renderers that expand in the vertex shader): bits 0-4 x, 5-9 z, 10-14 y (= voxel idx),
+// 15-17 face (VX_LEFT..VX_UP), 18 block type (0 GRASS, 1 DIRT); the chunk is implied by offsets[].
+template <bool PACKED>
 __global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
 {
@@ -528,10 +535,12 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     uint32_t it = 0;
 
     for (uint32_t tile = wid + part * kEmitWarps; tile < n_tiles; tile += kEmitWarps * kEmitSplit, ++it) {
-        uint32_t *stg = s.stage[wid][it % kStageBufs];
-        // the bulk store that last read this buffer (two tiles ago) must be done reading it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kStageBufs - 1) : "memory");
-        __syncwarp();
+        uint32_t *stg = PACKED ? nullptr : s.stage[wid][it % kStageBufs];
+        if (!PACKED) {
+            // the bulk store that last read this buffer (two tiles ago) must be done reading it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kStageBufs - 1) : "memory");
+            __syncwarp();
+        }
 
         const uint32_t q0 = tile << 5;
         const uint32_t nq = min(32u, count - q0);
@@ -574,6 +583,11 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
                 seen += bit;
             }
             const uint32_t type = typ_rows ? ((__ldg(typ_rows + r) >> x) & 1u) : 0u;
+            if (PACKED) {
+                // 128 B per warp, coalesced
+                out32[(a.offsets[m] - a.quad_base) + q] = (r << 5) | x | (face << 15) | (type << 18);
+                continue;
+            }
             const uint32_t tf = type * 8u + face;
             const uint4 *L = reinterpret_cast<const uint4 *>(&s.lut[tf * kLutStride]);
             const uint4 c0v = L[0], c1v = L[1], c2v = L[2];
@@ -587,6 +601,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
             w[15] = VX_1;
             w[16] = s.lut[tf * kLutStride + 16];
         }
+        if (PACKED) continue;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
         __syncwarp();
         const uint32_t nwords = nq * 17u;
@@ -608,7 +623,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
             for (uint32_t i = lane; i < nwords; i += 32u) out32[G + i] = stg[lead + i];
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+    if (!PACKED && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
 }
 
 }  // namespace
@@ -684,12 +699,15 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(EmitSmem));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    vx_mesh_emit_kernel<<<len * kEmitSplit, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+    if (a.packed)
+        vx_mesh_emit_kernel<true><<<len * kEmitSplit, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
+    else
+        vx_mesh_emit_kernel<false><<<len * kEmitSplit, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

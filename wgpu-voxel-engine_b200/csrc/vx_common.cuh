@@ -49,7 +49,8 @@ struct vx_mesh_args {
     const uint8_t *mesh_mask;   // [n] or nullptr
     uint32_t *counts;           // [n]
     uint64_t *offsets;          // [n+1]
-    vx_instance *out;
+    vx_instance *out;           // (uint32_t * when packed)
+    int packed;                 // emit 32-bit quad records instead of 68-byte instances
     unsigned long long capacity;
     uint32_t *status;           // optional
     uint32_t *ticket;           // count kernel: zero-initialised CTA ticket (last CTA runs the scan)

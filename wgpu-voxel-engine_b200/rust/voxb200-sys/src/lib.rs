@@ -60,6 +60,13 @@ extern "C" {
     pub fn vx_gen_mesh(ctx: *mut vx_ctx, coords: *const i32, n: usize, params: *const vx_noise_params,
                        nbr_mask: *const u8, counts: *mut u32, offsets: *mut u64, instances: *mut vx_instance,
                        capacity: usize, total_out: *mut u64, blocks_out: *mut u8) -> c_int;
+    pub fn vx_gen_mesh_packed(ctx: *mut vx_ctx, coords: *const i32, n: usize, params: *const vx_noise_params,
+                              nbr_mask: *const u8, counts: *mut u32, offsets: *mut u64, quads: *mut u32,
+                              capacity: usize, total_out: *mut u64) -> c_int;
+    pub fn vx_gen_mesh_packed_device(ctx: *mut vx_ctx, coords: *const i32, n: usize,
+                                     params: *const vx_noise_params, nbr_mask: *const u8, counts: *mut u32,
+                                     offsets: *mut u64, quads: *mut u32, capacity: usize, status: *mut u32,
+                                     stream: *mut c_void) -> c_int;
     pub fn vx_planes_from_matrix(m: *const f32, planes: *mut f32) -> c_int;
     pub fn vx_frustum_cull(ctx: *mut vx_ctx, planes: *const f32, n_frames: usize, coords: *const i32, n: usize,
                            visible: *mut u8) -> c_int;

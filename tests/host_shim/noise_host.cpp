@@ -9,6 +9,7 @@
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __float2int_rz(float f) { return (int)f; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -39,7 +40,8 @@ extern "C" void shim_noise_chunk(const int32_t *c, int32_t seed, float freq, flo
 }
 
 // the sign-only (coefficient-table) variant used by vx_fill_brick_kernel
-extern "C" void shim_noise_chunk_sign(const int32_t *c, int32_t seed, float freq, float gain, float lac, float *out)
+template <bool FUSED>
+static void noise_chunk_sign(const int32_t *c, int32_t seed, float freq, float gain, float lac, float *out)
 {
     float4 lut[VXN_LUT_FLOAT4S];
     for (uint32_t i = 0; i < VXN_LUT_FLOAT4S; ++i) lut[i] = vxn_grad_coeffs(i >> 3);
@@ -52,12 +54,23 @@ extern "C" void shim_noise_chunk_sign(const int32_t *c, int32_t seed, float freq
             const float4 *ll = lut + (lane & 7);
             for (int y = 0; y < 32; ++y) {
                 float x = sx * freq, yy = sy * freq, z = (oz + (float)y) * freq, amp = 1.0f;
-                float r = vxn_simplex3_sign(x, yy, z, x + yy, (uint32_t)seed, ll);
+                float r = vxn_simplex3_sign<FUSED>(x, yy, z, x + yy, (uint32_t)seed, ll);
                 for (int o = 1; o < 3; ++o) {
                     x *= lac; yy *= lac; z *= lac; amp *= gain;
-                    r = vxn_simplex3_sign(x, yy, z, x + yy, (uint32_t)seed, ll) * amp + r;
+                    r = vxn_simplex3_sign<FUSED>(x, yy, z, x + yy, (uint32_t)seed, ll) * amp + r;
                 }
                 out[lane + 32 * zz + 1024 * y] = r;
             }
         }
 }
+
+extern "C" void shim_noise_chunk_sign(const int32_t *c, int32_t seed, float freq, float gain, float lac, float *out)
+{
+    noise_chunk_sign<false>(c, seed, freq, gain, lac, out);
+}
+// fused (FMA) evaluation of the smooth part: NOT bit-equal, bounded difference
+extern "C" void shim_noise_chunk_fused(const int32_t *c, int32_t seed, float freq, float gain, float lac, float *out)
+{
+    noise_chunk_sign<true>(c, seed, freq, gain, lac, out);
+}
+extern "C" float shim_fused_err_ulps(void) { return VXN_FUSED_ERR_ULPS; }

@@ -19,6 +19,8 @@ def shim(tmp_path_factory):
     L = C.CDLL(so)
     L.shim_noise_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.shim_noise_chunk_sign.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.shim_noise_chunk_fused.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.shim_fused_err_ulps.restype = C.c_float
     return L
 
 
@@ -53,3 +55,23 @@ def test_sign_only_gradient_variant(shim, oracle, coord, seed, gain, lac, freq):
     nz = want != 0
     assert np.array_equal(out.view(np.uint32)[nz], want.view(np.uint32)[nz])
     assert np.array_equal(out < 0, want < 0)
+
+
+def test_fused_evaluation_stays_inside_its_certified_bound(shim, oracle):
+    """The FMA evaluation used for sign decisions differs from the exact noise by far less than the
+    margin the kernel demands before trusting it."""
+    eps = 2.0 ** -24
+    ulps = float(shim.shim_fused_err_ulps())
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for coord in [(0, 0, 0), (511, 0, -512), (-77, 2, 33)] + [tuple(int(v) for v in rng.integers(-9000, 9000, 3)) for _ in range(9)]:
+        c = np.array(coord, np.int32)
+        out = np.empty(32768, np.float32)
+        shim.shim_noise_chunk_fused(c.ctypes.data, 1, 0.09, 2.5, 0.5, out.ctypes.data)
+        want = oracle.noise_chunk(coord)
+        worst = max(worst, float(np.max(np.abs(out.astype(np.float64) - want.astype(np.float64)))))
+    amps = 1 + 2.5 + 6.25
+    bound = (ulps * amps + 2 * amps) * eps           # per-octave bound x amplitudes + FBM roundings
+    assert worst <= bound, (worst, bound)
+    assert worst > 0                                  # it really is a different rounding sequence
+    print("max |fused - exact| = %.3g, certified bound %.3g, kernel margin %.3g" % (worst, bound, 3 * bound))

@@ -191,26 +191,37 @@ vx_fill_brick_kernel(const vx_fill_args a)
     const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
     const float thr1 = a.thr1, thr2 = a.thr2;
 
+    const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
 #pragma unroll 1
     for (uint32_t it = 0; it < 16u; ++it) {
         const uint32_t y = 2u * it + yy;
         const float z0 = __fmul_rn(__fadd_rn(oz, (float)y), freq);
         const float z1 = __fmul_rn(z0, lac);
         const float z2 = __fmul_rn(z1, lac);
-        const float u = __fmul_rn(vxn_simplex3_sign(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
-        bool solid;
-        if (__all_sync(VX_FULL, fabsf(u) > thr2)) {
+        // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
+        bool solid, certain;
+        const float u = __fmul_rn(vxn_simplex3_sign<true>(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
+        if (__all_sync(VX_FULL, fabsf(u) > thr2 + errm)) {
             solid = u < 0.0f;
+            certain = true;
         } else {
-            const float t = __fmul_rn(vxn_simplex3_sign(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1);
-            const float ut = __fadd_rn(u, t);
-            if (__all_sync(VX_FULL, fabsf(ut) > thr1)) {
+            const float ut = __fmaf_rn(vxn_simplex3_sign<true>(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1, u);
+            if (__all_sync(VX_FULL, fabsf(ut) > thr1 + errm)) {
                 solid = ut < 0.0f;
+                certain = true;
             } else {
-                const float s1 = vxn_simplex3_sign(hx[0], hy[0], z0, hxy[0], seed, lut_lane);
-                // reference association: r = s1; r = t + r; r = u + r
-                solid = __fadd_rn(u, __fadd_rn(t, s1)) < 0.0f;
+                const float r = __fadd_rn(ut, vxn_simplex3_sign<true>(hx[0], hy[0], z0, hxy[0], seed, lut_lane));
+                solid = r < 0.0f;
+                certain = fabsf(r) > errm;
             }
+        }
+        if (__any_sync(VX_FULL, !certain)) {
+            // some lane is within the margin of zero: redo the step with the reference's exact
+            // operation order (separately rounded, r = u + (t + s1))
+            const float ue = __fmul_rn(vxn_simplex3_sign<false>(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
+            const float te = __fmul_rn(vxn_simplex3_sign<false>(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1);
+            const float s1 = vxn_simplex3_sign<false>(hx[0], hy[0], z0, hxy[0], seed, lut_lane);
+            solid = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
         }
         const uint32_t word = __ballot_sync(VX_FULL, solid);     // bit = yy*16 + zz*4 + xx
         if (lane < 8u) nib[2u * it + (lane >> 2)][lane & 3u][xblk] = (uint8_t)((word >> (4u * lane)) & 15u);
@@ -288,6 +299,9 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
         const float slack = 1.0f + 1e-5f * (1.0f + g1 + g2);
         b.thr1 = 0.0306f * slack;
         b.thr2 = 0.0306f * (1.0f + g1) * slack;
+        // |fused - exact| <= VXN_FUSED_ERR_ULPS * 2^-24 per octave value, times the
+        // octave amplitudes, plus the roundings of the FBM combination; x3 slack on top.
+        b.err_margin = 3.0f * (VXN_FUSED_ERR_ULPS * (1.0f + g1 + g2) + 2.0f * (1.0f + g1 + g2)) * 5.9604645e-8f;
         const uint32_t n_items = a.max_units / 32u;
         if (a.blocks) vx_fill_brick_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
         else vx_fill_brick_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);

@@ -133,16 +133,40 @@ typedef const float4 *vxn_lut_ref;          // host build (tests/host_shim): pla
 static inline float4 vxn_lut_load(vxn_lut_ref lut_lane, uint32_t t) { return lut_lane[(t & 15u) * 8u]; }
 #endif
 
+// FUSED = false: separately rounded ops, bit-equal to the exact noise up to the sign of zero.
+// FUSED = true : same cell selection, but weights / gradient dots / sums use FMA (fewer
+//                instructions, different roundings).  |fused - exact| <= VXN_FUSED_ERR_ULPS * 2^-24
+//                per simplex_3d value (bound derived in DESIGN.md 4.1), so a fused result is only
+//                trusted for a SIGN decision when it clears that margin; otherwise the caller
+//                re-evaluates with FUSED = false.
+#define VXN_FUSED_ERR_ULPS 5.4f
+
+template <bool FUSED>
 __device__ __forceinline__ float vxn_grad_lut(uint32_t h, float x, float y, float z, vxn_lut_ref lut_lane)
 {
     h = ((h * h) * 60493u) * h;
     const float4 c = vxn_lut_load(lut_lane, (uint32_t)(((int32_t)h) >> 13) ^ h);    // entry (.. & 15)
+    if (FUSED) return __fmaf_rn(c.z, z, __fmaf_rn(c.y, y, __fmul_rn(c.x, x)));
     return __fadd_rn(__fadd_rn(__fmul_rn(c.x, x), __fmul_rn(c.y, y)), __fmul_rn(c.z, z));
 }
 
+template <bool FUSED>
+__device__ __forceinline__ float vxn_weight_t(float a, float b, float c)
+{
+    float t;
+    if (FUSED) t = __fmaf_rn(-c, c, __fmaf_rn(-b, b, __fmaf_rn(-a, a, 0.6f)));
+    else t = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(a, a)), __fmul_rn(b, b)), __fmul_rn(c, c));
+    t = fmaxf(t, 0.0f);
+    t = __fmul_rn(t, t);
+    return __fmul_rn(t, t);
+}
+
+template <bool FUSED>
 __device__ __forceinline__ float vxn_simplex3_sign(float x, float y, float z, float xy, uint32_t seed,
                                                    vxn_lut_ref lut_lane)
 {
+    // ---- cell selection: ALWAYS the reference's exact operation sequence, so the fused and the
+    //      exact evaluation pick the same simplex and the same corner order ----------------------
     const float f = __fmul_rn(VXN_F3, __fadd_rn(xy, z));
     const float xf = floorf(__fadd_rn(x, f));
     const float yf = floorf(__fadd_rn(y, f));
@@ -173,11 +197,14 @@ __device__ __forceinline__ float vxn_simplex3_sign(float x, float y, float z, fl
     const float y3 = __fadd_rn(y0, VXN_G33);
     const float z3 = __fadd_rn(z0, VXN_G33);
 
-    const float v0 = __fmul_rn(vxn_weight(x0, y0, z0), vxn_grad_lut(ia ^ ja ^ ka, x0, y0, z0, lut_lane));
-    const float v1 = __fmul_rn(vxn_weight(x1, y1, z1),
-                               vxn_grad_lut((i1 ? ib : ia) ^ (j1 ? jb : ja) ^ (k1 ? kb : ka), x1, y1, z1, lut_lane));
-    const float v2 = __fmul_rn(vxn_weight(x2, y2, z2),
-                               vxn_grad_lut((i2 ? ib : ia) ^ (j2 ? jb : ja) ^ (k2 ? kb : ka), x2, y2, z2, lut_lane));
-    const float v3 = __fmul_rn(vxn_weight(x3, y3, z3), vxn_grad_lut(ib ^ jb ^ kb, x3, y3, z3, lut_lane));
+    // ---- smooth part --------------------------------------------------------------------------
+    const float w0 = vxn_weight_t<FUSED>(x0, y0, z0), g0 = vxn_grad_lut<FUSED>(ia ^ ja ^ ka, x0, y0, z0, lut_lane);
+    const float w1 = vxn_weight_t<FUSED>(x1, y1, z1),
+                g1 = vxn_grad_lut<FUSED>((i1 ? ib : ia) ^ (j1 ? jb : ja) ^ (k1 ? kb : ka), x1, y1, z1, lut_lane);
+    const float w2 = vxn_weight_t<FUSED>(x2, y2, z2),
+                g2 = vxn_grad_lut<FUSED>((i2 ? ib : ia) ^ (j2 ? jb : ja) ^ (k2 ? kb : ka), x2, y2, z2, lut_lane);
+    const float w3 = vxn_weight_t<FUSED>(x3, y3, z3), g3 = vxn_grad_lut<FUSED>(ib ^ jb ^ kb, x3, y3, z3, lut_lane);
+    if (FUSED) return __fmaf_rn(w0, g0, __fmaf_rn(w1, g1, __fmaf_rn(w2, g2, __fmul_rn(w3, g3))));
+    const float v0 = __fmul_rn(w0, g0), v1 = __fmul_rn(w1, g1), v2 = __fmul_rn(w2, g2), v3 = __fmul_rn(w3, g3);
     return __fadd_rn(__fadd_rn(__fadd_rn(v3, v2), v1), v0);
 }

@@ -114,7 +114,8 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
  * Outputs: counts uint32[n], offsets uint64[n+1] (exclusive scan of counts),
  * instances[capacity] in list order, each chunk's quads in the reference's
  * emission order ((y,z,x)-major, then LEFT,RIGHT,BACK,FRONT,DOWN,UP).
- * instances may be NULL (count only).  total_out receives offsets[n]. */
+ * instances may be NULL (count only).  total_out receives offsets[n].
+ * (Runs on the context's first GPU: the call is PCIe-bound on the 32 KiB/chunk upload.) */
 int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
             const int32_t *nbr_idx, const uint8_t *mesh_mask,
             uint32_t *counts, uint64_t *offsets,

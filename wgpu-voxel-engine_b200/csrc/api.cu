@@ -349,6 +349,7 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
         d.id = ids[i];
         cudaError_t e = cudaSetDevice(d.id);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.id);
+        if (e == cudaSuccess) e = vx_init_mesh_kernels();
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
         for (int b = 0; b < 2 && e == cudaSuccess; ++b) {

@@ -648,16 +648,7 @@ cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t
         vx_resolve_args b = a;
         b.table_size = 64;
         while (b.table_size < 2 * a.n) b.table_size <<= 1;
-        const size_t smem = (size_t)b.table_size * 4 + (size_t)a.n * 12;      // <= 32 KB + 48 KB
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 64 && !configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));
-            if (e != cudaSuccess) return e;
-            configured[dev] = true;
-        }
+        const size_t smem = (size_t)b.table_size * 4 + (size_t)a.n * 12;      // <= 32 KB + 48 KB (vx_init_mesh_kernels)
         vx_resolve_small_kernel<<<1, 1024, smem, s>>>(b);
         if (launches) ++*launches;
         return cudaGetLastError();
@@ -695,19 +686,21 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
 {
     if (len == 0) return cudaSuccess;
     static_assert(sizeof(EmitSmem) <= 64 * 1024, "emit kernel shared memory budget");
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(EmitSmem));
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
     if (a.packed)
         vx_mesh_emit_kernel<true><<<len * kEmitSplit, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
     else
         vx_mesh_emit_kernel<false><<<len * kEmitSplit, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     if (launches) ++*launches;
     return cudaGetLastError();
+}
+
+// Per-device kernel attributes (dynamic shared memory above 48 KB); called by vx_create with
+// the device current.
+cudaError_t vx_init_mesh_kernels()
+{
+    cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(EmitSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));
 }

@@ -81,4 +81,6 @@ cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_
 cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
                               uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches);
 
+cudaError_t vx_init_mesh_kernels();
+
 cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, uint64_t *launches);

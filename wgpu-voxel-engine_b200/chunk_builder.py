@@ -1,0 +1,215 @@
+"""Batched host mirror of the reference's chunk scheduler (chunk_builder.rs, world.rs, player.rs).
+
+The reference dispatches ONE queued chunk per tick (chunk_builder.rs:75-76, engine.rs:23) and ONE
+remesh per tick (:96-98), so a ring of ~80 chunks takes hundreds of ticks to settle.  This mirror
+keeps the reference's decisions -- which chunks are wanted (primary 3x3 on entering a new chunk
+:171-215; frustum-gated rings 2..RENDER_DISTANCE-1 :217-255), which loaded chunks must be re-meshed
+(the four neighbours of every arrival, :269-300), what is evicted (:334-352) -- but hands the whole
+visible-set delta to the GPU in one call:
+
+    one  Frustum.contains_many   (vx_frustum_cull)   for the enqueue gate
+    one  Context.gen_mesh        (vx_gen_mesh)       for every new chunk AND every re-mesh
+
+After that single call the world equals the state the reference reaches once its queues drain when
+its workers finish within the tick (tests/test_scheduler.py, against a tick-by-tick restatement of
+the reference).  With slower workers the reference itself is racy -- a chunk dispatched while an
+adjacent one is in flight keeps stale, hidden border faces (chunk_builder.rs:77-80 vs :318-321,
+shown by test_reference_scheduler_race_with_slow_workers) -- and that artefact is not reproduced.
+SURVEY.md section 8(f) rank 1.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .chunk import Chunk, ChunkMesh
+from .context import Context, default_context
+from .coordinate import ChunkCoord3D
+from .frustum_culling import Frustum
+
+RENDER_DISTANCE = 5          # world.rs:19
+Coord = Tuple[int, int, int]
+
+
+class World:
+    """world.rs:14-17"""
+
+    def __init__(self):
+        self.chunks: Dict[Coord, Chunk] = {}
+        self.meshes: Dict[Coord, ChunkMesh] = {}
+
+
+class Player:
+    """player.rs: position -> chunk coordinate, 'entered a new chunk' predicate."""
+
+    def __init__(self, eye):
+        self.pos = tuple(float(v) for v in eye)
+        self.chunk = self._to_chunk(self.pos)                      # player.rs:10-14
+
+    @staticmethod
+    def _to_chunk(p) -> Coord:
+        return tuple(int(np.floor(v)) >> 5 for v in p)             # coordinate.rs:33-38
+
+    def update_pos(self, eye):
+        self.pos = tuple(float(v) for v in eye)                    # player.rs:16-18
+
+    def is_in_new_chunk_pos(self) -> bool:
+        return self.chunk != self._to_chunk(self.pos)              # player.rs:24-27
+
+    def update_chunk_pos(self):
+        self.chunk = self._to_chunk(self.pos)                      # player.rs:20-22
+
+
+def primary_coords(pc: Coord) -> List[Coord]:
+    """chunk_builder.rs:178-214: centre first, then the radius-1 ring in the reference's order."""
+    px, _, pz = pc
+    out = [(px, 0, pz)]
+    r = 1
+    for z in range(-r, r + 1):
+        out += [(px + r, 0, pz + z), (px - r, 0, pz + z)]
+    for x in range(-r + 1, r):
+        out += [(px + x, 0, pz + r), (px + x, 0, pz - r)]
+    return out
+
+
+def ring_coords(pc: Coord) -> List[Coord]:
+    """chunk_builder.rs:217-247: rings 2..RENDER_DISTANCE-1 in the reference's enumeration order."""
+    px, _, pz = pc
+    out = []
+    for r in range(2, RENDER_DISTANCE):
+        for z in range(-r, r + 1):
+            out += [(px + r, 0, pz + z), (px - r, 0, pz + z)]
+        for x in range(-r + 1, r):
+            out += [(px + x, 0, pz + r), (px + x, 0, pz - r)]
+    return out
+
+
+def neighbours(c: Coord) -> List[Coord]:
+    """chunk_builder.rs:134-169 order: -x, +x, -z, +z."""
+    x, y, z = c
+    return [(x - 1, y, z), (x + 1, y, z), (x, y, z - 1), (x, y, z + 1)]
+
+
+class ChunkGenerator:
+    """mode = "reference": the world after this call is EXACTLY the one the reference settles in
+    (workers finishing within the tick), including its artefact: a chunk dispatched while an
+    adjacent chunk is still undelivered keeps the border faces towards it (the 9-chunk burst of
+    :178-214 is delivered one per tick, :311).  The queues are replayed symbolically on the host --
+    pure bookkeeping, no meshing -- to learn each chunk's neighbour snapshot at its last (re)build.
+    mode = "converged": every touched chunk is meshed against all loaded neighbours (no artefact)."""
+
+    def __init__(self, device: Optional[Context] = None, mode: str = "reference"):
+        assert mode in ("reference", "converged")
+        self._ctx = device
+        self.mode = mode
+        self.last_batch = 0          # chunks sent to the GPU by the last build_chunks
+        self.gpu_calls = 0
+        self.replayed_ticks = 0      # reference ticks the last call stood for
+
+    # ---- symbolic replay of chunk_builder.rs:45-352 ----------------------------------------------
+    def _replay(self, entered: bool, player: Player, loaded: set, visible_ring: List[Coord]):
+        """Returns {coord: neighbour mask at its last (re)build} for every chunk built or re-built,
+        and the final loaded set.  `loaded` is the post-eviction world."""
+        loaded = set(loaded)
+        snap: Dict[Coord, int] = {}
+        load_queue: List[Coord] = []
+        rebuild_queue: List[Coord] = []
+        in_process: List[Coord] = []
+        chan: List[Coord] = []                     # data channel, FIFO, one receive per tick (:311)
+        mesh_chan = 0
+
+        def mask_now(c):
+            return sum(1 << k for k, n in enumerate(neighbours(c)) if n in loaded)
+
+        def is_loaded(c):
+            return c in loaded or c in load_queue or c in in_process
+
+        def spawn(c):
+            snap[c] = mask_now(c)                  # adjacent_chunks snapshot at dispatch (:77, :122)
+            in_process.append(c)
+            chan.append(c)
+
+        ticks = 0
+        first = True
+        while True:
+            ticks += 1
+            if first and entered:                  # load_primary_chunks (:171-215)
+                for c in primary_coords(player.chunk):
+                    if not is_loaded(c):
+                        spawn(c)
+            first = False
+            for c in visible_ring:                 # enqueue_chunks_in_frustum (:217-255)
+                if not is_loaded(c):
+                    load_queue.append(c)
+            if load_queue:                         # process_chunk_loading_queue (:69-87)
+                spawn(load_queue.pop(0))
+            if not in_process and rebuild_queue:   # process_rebuild_queue (:89-112)
+                c = rebuild_queue.pop(0)
+                if c in loaded:
+                    snap[c] = mask_now(c)
+                    mesh_chan += 1
+            if chan:                               # update_world (:310-324)
+                c = chan.pop(0)
+                loaded.add(c)
+                in_process.remove(c)
+                x, y, z = c
+                for n in [(x + 1, y, z), (x - 1, y, z), (x, y, z + 1), (x, y, z - 1)]:   # :269-300
+                    if n in loaded:
+                        rebuild_queue.append(n)
+            if mesh_chan:                          # (:325-331)
+                mesh_chan -= 1
+            load_queue.clear()                     # clean_up_queues (:302-308)
+            rebuild_queue = sorted(set(rebuild_queue))
+            if not (in_process or rebuild_queue or chan or mesh_chan) and \
+                    all(c in loaded for c in visible_ring):
+                break
+            if ticks > 100000:
+                raise RuntimeError("scheduler replay did not settle")
+        self.replayed_ticks = ticks
+        return snap, loaded
+
+    def build_chunks(self, player: Player, world: World, frustum: Frustum) -> None:
+        """chunk_builder.rs:45-67, batched."""
+        ctx = self._ctx or default_context()
+        entered = player.is_in_new_chunk_pos()
+        if entered:
+            player.update_chunk_pos()
+        # filter_unseen_chunks (:334-352).  The reference evicts at the end of the tick in which the
+        # player chunk changed; every load after the first and every re-mesh is dispatched in a later
+        # tick, i.e. against the post-eviction world -- and no wanted chunk (<= 4 away) can touch an
+        # evicted one (> 5 away) -- so evicting first reproduces its settled state.
+        px, py, pz = player.chunk
+        for c in [c for c in world.chunks
+                  if not (abs(c[0] - px) <= RENDER_DISTANCE and abs(c[2] - pz) <= RENDER_DISTANCE
+                          and abs(c[1] - py) <= RENDER_DISTANCE)]:
+            del world.chunks[c]
+            world.meshes.pop(c, None)
+        # enqueue gate (:217-255): ONE batched frustum test instead of one contains() per coordinate
+        cand = [c for c in ring_coords(player.chunk) if c not in world.chunks]
+        visible_ring: List[Coord] = []
+        if cand:
+            vis = (Frustum(frustum.planes, ctx)).contains_many(np.array(cand, np.int32))
+            visible_ring = [c for c, v in zip(cand, vis) if v]
+        primaries = [c for c in primary_coords(player.chunk) if c not in world.chunks] if entered else []
+        if not visible_ring and not primaries:
+            self.last_batch = 0
+            self.replayed_ticks = 0
+            return
+        if self.mode == "reference":
+            snap, _ = self._replay(entered, player, set(world.chunks), visible_ring)
+        else:
+            wanted = list(dict.fromkeys(primaries + visible_ring))
+            present = set(world.chunks) | set(wanted)
+            touched = wanted + [n for c in wanted for n in neighbours(c) if n in world.chunks]
+            snap = {c: sum(1 << k for k, n in enumerate(neighbours(c)) if n in present)
+                    for c in dict.fromkeys(touched)}
+        batch = list(snap)
+        mask = np.array([snap[c] for c in batch], np.uint8)
+        res = ctx.gen_mesh(np.array(batch, np.int32), nbr_mask=mask, blocks=True)   # ONE GPU call
+        self.gpu_calls += 1
+        self.last_batch = len(batch)
+        for i, c in enumerate(batch):
+            if c not in world.chunks:                                   # update_world (:310-324)
+                world.chunks[c] = Chunk(ChunkCoord3D(*c), res.blocks[i])
+            world.meshes[c] = ChunkMesh(res.chunk(i).copy())            # and :325-331 for re-meshes

@@ -367,3 +367,85 @@ def test_packed_quads_expand_to_the_instance_stream(ctx, oracle):
     tex = np.array([[0, 0, 0, 0, 1, 2], [1, 1, 1, 1, 1, 1]], np.uint32)             # [type][face]: slots 0,1,2,3,5,4
     want["texture_index"] = tex[typ, face]
     assert _canon(full.instances).tobytes() == want.tobytes()
+
+
+def test_large_list_uses_the_global_hash_path(ctx, oracle):
+    """> 4096 chunks: neighbour resolution runs as vx_ht_insert + vx_resolve over a global-memory table
+    instead of the single-CTA shared-memory kernel.  Same answers as the small path and the oracle."""
+    coords = _grid(-36, -36, 72, 72)                      # 5184 chunks
+    big = ctx.gen_mesh(coords, instances=False)
+    assert big.total == int(big.counts.sum())
+    # the same region in two calls (small path each? no: 2592 each -> small path) with explicit masks
+    inside = np.zeros((74, 74), bool)
+    inside[1:-1, 1:-1] = True
+    ix, iz = coords[:, 0] + 37, coords[:, 2] + 37
+    mask = (inside[iz, ix - 1] * 1 + inside[iz, ix + 1] * 2 + inside[iz - 1, ix] * 4 + inside[iz + 1, ix] * 8).astype(np.uint8)
+    h = len(coords) // 2
+    a = ctx.gen_mesh(coords[:h], nbr_mask=mask[:h], instances=False)
+    b = ctx.gen_mesh(coords[h:], nbr_mask=mask[h:], instances=False)
+    assert np.array_equal(np.concatenate([a.counts, b.counts]), big.counts)
+    # and the large path with masks + halo slabs (present neighbours outside the list)
+    full_mask = np.full(len(coords), 15, np.uint8)
+    c = ctx.gen_mesh(coords, nbr_mask=full_mask, instances=False)
+    for i in (0, 71, 2600, 5183):
+        cubes = oracle.generate_terrain(coords[i])
+        adj_in = [oracle.generate_terrain(n) if (mask[i] >> k) & 1 else None for k, n in enumerate(_neighbours(coords[i]))]
+        assert big.counts[i] == len(oracle.cull_unseen_triangles(coords[i], cubes, adj_in))
+        adj_all = [oracle.generate_terrain(n) for n in _neighbours(coords[i])]
+        assert c.counts[i] == len(oracle.cull_unseen_triangles(coords[i], cubes, adj_all))
+    # duplicates in the list are legal: every copy gets the same mesh
+    dup = np.concatenate([coords[:3], coords[:3]])
+    d = ctx.gen_mesh(dup)
+    assert np.array_equal(d.counts[:3], d.counts[3:]) and d.chunk(0).tobytes() == d.chunk(3).tobytes()
+
+
+def test_device_entry_points_match_host_entry_points(ctx, vox):
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    ts = torch.cuda.Stream(device=dev)
+    st = ts.cuda_stream
+    coords = _grid(-2, 3, 3, 3, y=-1)
+    n = len(coords)
+    d_coords = torch.from_numpy(coords).to(dev)
+    # vx_fill_device
+    host = ctx.fill(coords, blocks=True, noise=True, occupancy=True, census=True)
+    d_blocks = torch.zeros(n * 32768, dtype=torch.uint8, device=dev)
+    d_noise = torch.zeros(n * 32768, dtype=torch.float32, device=dev)
+    d_occ = torch.zeros(n * 1024, dtype=torch.int32, device=dev)
+    d_nz = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.fill_device(d_coords.data_ptr(), n, blocks_ptr=d_blocks.data_ptr(), noise_ptr=d_noise.data_ptr(),
+                    occ_ptr=d_occ.data_ptr(), near_zero_ptr=d_nz.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_blocks.cpu().numpy().reshape(n, -1), host["blocks"])
+    assert np.array_equal(d_noise.cpu().numpy().view(np.uint32).reshape(n, -1), host["noise"].view(np.uint32))
+    assert np.array_equal(d_occ.cpu().numpy().view(np.uint32).reshape(n, -1), host["occupancy"])
+    assert int(d_nz.item()) == host["near_zero"]
+    # fast (sign-only) device fill gives the same blocks
+    d_blocks2 = torch.zeros_like(d_blocks)
+    ctx.fill_device(d_coords.data_ptr(), n, blocks_ptr=d_blocks2.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(d_blocks, d_blocks2)
+    # vx_mesh_device
+    hm = ctx.mesh(coords, host["blocks"])
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_inst = torch.zeros((hm.total + 3) * 17, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    ctx.mesh_device(d_coords.data_ptr(), n, d_blocks.data_ptr(), d_counts.data_ptr(), d_offsets.data_ptr(),
+                    d_inst.data_ptr(), hm.total + 3, status_ptr=d_status.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert int(d_status[0].item()) == 0
+    assert d_inst.cpu().numpy().view(np.uint8)[:hm.total * 68].tobytes() == hm.instances.tobytes()
+    # vx_frustum_cull_device, bytes and bits in one launch
+    planes = np.random.default_rng(2).standard_normal((5, 6, 4)).astype(np.float32)
+    planes[:, :, 3] += 150
+    hv = ctx.frustum_cull(planes, coords)
+    d_pl = torch.from_numpy(planes).to(dev)
+    d_vis = torch.zeros(5 * n, dtype=torch.uint8, device=dev)
+    d_bits = torch.zeros(5 * ((n + 31) // 32), dtype=torch.int32, device=dev)
+    ctx.frustum_cull_device(d_pl.data_ptr(), 5, d_coords.data_ptr(), n, visible_ptr=d_vis.data_ptr(),
+                            bits_ptr=d_bits.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_vis.cpu().numpy().reshape(5, n), hv)
+    bits = np.unpackbits(d_bits.cpu().numpy().view(np.uint8).reshape(5, -1), axis=1, bitorder="little")[:, :n]
+    assert np.array_equal(bits, hv)

@@ -86,8 +86,8 @@ float vxo_simplex_3d(float x, float y, float z, int32_t seed)
     z0 = z - (z0 - g);
 
     int xy = x0 >= y0, yz = y0 >= z0, xz = x0 >= z0;
-    int i1 = xy & xz, j1 = !xy & yz, k1 = !xz & !yz;
-    int i2 = xy | xz, j2 = !xy | yz, k2 = !(xz & yz);
+    int i1 = xy & xz, j1 = (!xy) & yz, k1 = (!xz) & (!yz);
+    int i2 = xy | xz, j2 = (!xy) | yz, k2 = !(xz & yz);
 
     float x1 = (x0 + (i1 ? -1.0f : 0.0f)) + G3;
     float y1 = (y0 + (j1 ? -1.0f : 0.0f)) + G3;

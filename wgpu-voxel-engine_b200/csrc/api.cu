@@ -80,8 +80,9 @@ constexpr size_t kSliceBytes = size_t(256) << 20;                      // stagin
 struct Dev {
     int id = 0;
     int n_sm = 148;
-    cudaStream_t stream = nullptr, copy = nullptr;
+    cudaStream_t stream = nullptr, copy = nullptr, aux = nullptr;
     cudaEvent_t emit_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join = nullptr;   // aux stream: neighbour resolve + halo fill beside the main fill
     DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_in, counts, offsets, small, blocks, noise,
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
@@ -194,7 +195,21 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     if (n == 0) return VX_OK;
     CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
     const bool may_halo = d_mask_all != nullptr || lo != 0 || hi != n_all;
-    RET(dev_resolve(d, s, d_coords_all, n_all, lo, hi, d_mask_all, may_halo));
+    // Neighbour resolution and the halo slabs depend only on the coordinates: they run on the
+    // auxiliary stream beside the (400 us) main fill and join before the count kernel.
+    CK(cudaEventRecord(d.fork, s));
+    CK(cudaStreamWaitEvent(d.aux, d.fork, 0));
+    RET(dev_resolve(d, d.aux, d_coords_all, n_all, lo, hi, d_mask_all, may_halo));
+    if (may_halo) {
+        vx_fill_args h{};
+        h.halo_items = d.halo_items.as<vx_halo_item>();
+        h.halo_count = d.halo_count();
+        h.max_units = n * 4u;
+        h.p = p;
+        h.occ = d.halo.as<uint32_t>();
+        TIMED(d, d.aux, VX_K_HALO, vx_launch_fill(h, true, d.aux, &d.launches));
+    }
+    CK(cudaEventRecord(d.join, d.aux));
 
     vx_fill_args f{};
     f.coords = d_coords_all + 3 * (size_t)lo;
@@ -203,15 +218,7 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     f.occ = d.occ.as<uint32_t>();
     f.blocks = d_blocks;
     TIMED(d, s, VX_K_FILL, vx_launch_fill(f, false, s, &d.launches));
-    if (may_halo) {
-        vx_fill_args h{};
-        h.halo_items = d.halo_items.as<vx_halo_item>();
-        h.halo_count = d.halo_count();
-        h.max_units = n * 4u;
-        h.p = p;
-        h.occ = d.halo.as<uint32_t>();
-        TIMED(d, s, VX_K_HALO, vx_launch_fill(h, true, s, &d.launches));
-    }
+    CK(cudaStreamWaitEvent(s, d.join, 0));
     vx_mesh_args m{};
     m.occ = d.occ.as<uint32_t>();
     m.typ = nullptr;
@@ -352,6 +359,9 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
         if (e == cudaSuccess) e = vx_init_mesh_kernels();
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming);
         for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
             e = cudaEventCreateWithFlags(&d.emit_done[b], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.d2h_done[b], cudaEventDisableTiming);
@@ -391,6 +401,9 @@ void vx_destroy(vx_ctx *ctx)
         }
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.copy) cudaStreamDestroy(d.copy);
+        if (d.aux) cudaStreamDestroy(d.aux);
+        if (d.fork) cudaEventDestroy(d.fork);
+        if (d.join) cudaEventDestroy(d.join);
     }
     delete ctx;
 }

@@ -449,3 +449,34 @@ def test_device_entry_points_match_host_entry_points(ctx, vox):
     assert np.array_equal(d_vis.cpu().numpy().reshape(5, n), hv)
     bits = np.unpackbits(d_bits.cpu().numpy().view(np.uint8).reshape(5, -1), axis=1, bitorder="little")[:, :n]
     assert np.array_equal(bits, hv)
+
+
+def test_host_streaming_reuses_arenas_correctly(ctx, vox):
+    """~14 M quads = 4+ slices through the two 256 MiB instance arenas: every arena is reused while
+    the copy stream is still draining the other one.  Must equal the single-launch device path."""
+    torch = pytest.importorskip("torch")
+    coords = _grid(-32, -24, 64, 48)                       # 3072 chunks
+    host = ctx.gen_mesh(coords)
+    assert host.total * 68 > 3 * (256 << 20)
+    dev = torch.device("cuda:0")
+    ts = torch.cuda.Stream(device=dev)
+    n = len(coords)
+    d_coords = torch.from_numpy(coords).to(dev)
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_inst = torch.zeros(host.total * 17, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    ctx.gen_mesh_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_offsets.data_ptr(), d_inst.data_ptr(),
+                        host.total, status_ptr=d_status.data_ptr(), stream=ts.cuda_stream)
+    torch.cuda.synchronize()
+    assert int(d_status[0].item()) == 0
+    assert np.array_equal(d_offsets.cpu().numpy().view(np.uint64), host.offsets)
+    got = d_inst.cpu().numpy().view(np.uint8)
+    want = host.instances.view(np.uint8).reshape(-1)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # boundary sizes around the shared-memory / global-memory resolve switch (4096)
+    for m in (4095, 4096, 4097):
+        c = _grid(-40, -30, 80, 60)[:m]
+        a = ctx.gen_mesh(c, instances=False)
+        b = ctx.gen_mesh(c[::-1].copy(), instances=False)          # order must not matter for the counts
+        assert np.array_equal(a.counts, b.counts[::-1])

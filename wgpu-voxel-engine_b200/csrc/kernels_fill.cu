@@ -292,7 +292,7 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
     //  |world * freq * lac^k| <= 2^31 * |freq| * max(1, lac^2) must not overflow f32)
     const float reach = 2147483648.0f * fabsf(a.p.freq) * fmaxf(1.0f, a.p.lacunarity * a.p.lacunarity);
     const bool tame = isfinite(reach) && reach < 1e30f && isfinite(a.p.gain);
-    if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && !a.force_exact && tame) {
+    if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && tame) {
         vx_fill_args b = a;
         // |simplex_3d| <= 0.030585; 0.0306 plus a relative slack far above the f32 rounding of u, t, u+t
         const float g1 = fabsf(a.p.gain), g2 = fabsf(a.p.gain * a.p.gain);

@@ -37,7 +37,6 @@ struct vx_fill_args {
     unsigned long long *near_zero;    // optional counter
     float thr1, thr2;                 // sign-only shortcuts (set by the launcher)
     float err_margin;                 // certified |fused - exact| bound (set by the launcher)
-    int force_exact;                  // 1: always evaluate every octave (testing / A-B)
 };
 cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, uint64_t *launches);
 

@@ -307,6 +307,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "sample": "%d rings of 32x32 chunks (%.1f s wall), C oracle port of the reference work function "
                          "with AVX2 noise lanes, one chunk per task on %d threads" % (reps, dt, cores)}
 
+    # ---- live parity spot check: per-chunk quad counts of the first timed ring, GPU vs oracle ----
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        g = ctx.gen_mesh(h_coords[W], instances=False)
+        o = oracle.gen_mesh_batch(h_coords[W], want_instances=False)
+        parity = {"ring_step": W, "gpu_quads": g.total, "oracle_quads": o["total"],
+                  "per_chunk_counts_equal": bool(np.array_equal(g.counts, o["counts"]))}
+
     census = None
     try:
         census = ctx.fill(h_coords[W], blocks=False, census=True)["near_zero"]
@@ -353,6 +362,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "peaks": {"fp32_ffma_tflops": ffma_peak, "fp32_fmul_fadd_tflops": nofuse_peak, "int32_tops": int_peak,
                   "hbm_gbs": hbm_peak},
         "cpu_baseline": cpu,
+        "parity_spot_check": parity,
         "near_threshold_voxels": {"abs_noise_le_1e-6": census, "of": n * VOXELS},
     }
     emit_json(line)

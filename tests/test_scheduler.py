@@ -102,6 +102,9 @@ def test_batched_scheduler_reaches_the_reference_state(vox, oracle):
         for pos in ref.chunks:
             assert np.array_equal(world.chunks[pos].cubes, ref.chunks[pos])
             assert _canon(world.meshes[pos].instance_buffer).tobytes() == _canon(ref.meshes[pos]).tobytes(), pos
+        # draw gate (world.rs:34-37), one launch for all meshes == per-mesh Frustum::contains
+        drawn = world.visible_meshes(vox.Frustum(planes, ctx), ctx)
+        assert drawn == [p for p in world.meshes if oracle.frustum_contains(planes, p)]
     print("reference: %d ticks (x7 frames) to settle 3 poses; batched: %d GPU calls" % (total_ticks, gen.gpu_calls))
     # the artefact-free mode: every touched chunk meshed against all loaded neighbours
     gen2, world2, player2 = vox.ChunkGenerator(ctx, mode="converged"), vox.World(), vox.Player(POSES[0][0])

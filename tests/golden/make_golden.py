@@ -147,7 +147,19 @@ def chunk_record(coord):
     idx, face = np.nonzero(flat)
     stream = (idx.astype(np.uint32) * 8 + face.astype(np.uint32)).astype("<u4")
     sample = noise[::997]
+    # full InstanceRaw stream (quad.rs:47-54, renderer/instance.rs:1-6) built independently:
+    # t_matrix[c][r] = column c of R(face) for c < 3, (x, y, z, 1) for c = 3; texture per slot
+    rot = _rotation_matrices()
+    tex_of_face = np.array([0, 0, 0, 0, 1, 2], np.uint32)     # GRASS [0,0,0,0,2,1] via slots 0,1,2,3,5,4
+    inst = np.zeros(len(idx), dtype=[("t_matrix", "<f4", (4, 4)), ("texture_index", "<u4")])
+    inst["t_matrix"][:, :3, :3] = np.transpose(rot[face], (0, 2, 1))
+    inst["t_matrix"][:, 3, 0] = cx * 32 + (idx & 31)
+    inst["t_matrix"][:, 3, 1] = cy * 32 + (idx >> 10)
+    inst["t_matrix"][:, 3, 2] = cz * 32 + ((idx >> 5) & 31)
+    inst["t_matrix"][:, 3, 3] = 1.0
+    inst["texture_index"] = tex_of_face[face]
     return {
+        "instances_crc32_all": "%08x" % zlib.crc32(inst.tobytes()),
         "coord": list(coord),
         "solid": int(solid.sum()),
         "occ_crc32": "%08x" % zlib.crc32(occ.tobytes()),
@@ -174,6 +186,12 @@ SURVEY_APP_A = [   # SURVEY.md App. A table (third restatement)
      "faces_none": [1507, 1507, 957, 957, 1160, 1160], "faces_all": [726, 962, 845, 592, 1160, 1160],
      "noise_1000": "3d7a96d7"},
 ]
+
+
+def _rotation_matrices():
+    """[face][row][col] float32, faces L R B F D U, signed zeros canonicalised."""
+    r = rotations()
+    return np.stack([np.array([int(h, 16) for h in r[str(f)]], np.uint32).view(f32).reshape(3, 3) for f in range(6)])
 
 
 def rotations():

@@ -59,6 +59,11 @@ def test_fill_golden_crc(ctx, golden):
     # fast kernel variant (no noise output) must give the same blocks
     res2 = ctx.fill([r["coord"] for r in recs], blocks=True)
     assert np.array_equal(res2["blocks"], res["blocks"])
+    # full InstanceRaw streams against the numpy restatement (no oracle involved)
+    for r in recs:
+        m = ctx.gen_mesh([r["coord"]], nbr_mask=[15])
+        assert np.bincount(np.zeros(1, int)).size and m.total == sum(r["faces_all"])
+        assert "%08x" % zlib.crc32(_canon(m.instances).tobytes()) == r["instances_crc32_all"]
 
 
 @pytest.mark.parametrize("seed,octaves,freq", [(2, 3, 0.09), (12345, 1, 0.9), (1, 4, 0.05), (7, 2, 0.09)])

@@ -43,6 +43,10 @@ def test_numpy_golden_chunks(oracle, golden):
         idx = (q["x"] - w[0]) + 32 * (q["z"] - w[2]) + 1024 * (q["y"] - w[1])
         stream = (idx.astype(np.uint32) * 8 + q["face"]).astype("<u4")
         assert "%08x" % zlib.crc32(stream.tobytes()) == rec["quad_stream_crc32_all"]
+        # the full 68-byte instance stream against the numpy restatement's packing
+        inst = oracle.create_mesh(c, cubes, adj)
+        inst["t_matrix"] += np.float32(0)
+        assert "%08x" % zlib.crc32(inst.tobytes()) == rec["instances_crc32_all"]
         q0 = oracle.cull_unseen_triangles(c, cubes, None)
         assert np.bincount(q0["face"], minlength=6).tolist() == rec["faces_none"]
 

@@ -485,3 +485,28 @@ def test_host_streaming_reuses_arenas_correctly(ctx, vox):
         a = ctx.gen_mesh(c, instances=False)
         b = ctx.gen_mesh(c[::-1].copy(), instances=False)          # order must not matter for the counts
         assert np.array_equal(a.counts, b.counts[::-1])
+
+
+def test_host_api_output_slicing(ctx, oracle):
+    """Outputs larger than the 256 MiB staging buffers go through the slice loops of vx_fill and
+    vx_frustum_cull; sampled against the oracle."""
+    # vx_fill: 2200 chunks x (128 KiB noise + 32 KiB blocks + 4 KiB occupancy) = 360 MB -> 2 slices
+    coords = _grid(-25, -22, 50, 44)
+    res = ctx.fill(coords, blocks=True, noise=True, occupancy=True)
+    for i in (0, 1637, 1638, 1639, 2199):
+        want = oracle.noise_chunk(coords[i])
+        assert np.array_equal(res["noise"][i].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(res["blocks"][i], oracle.terrain_from_noise(want))
+        bits = np.unpackbits(res["occupancy"][i].view(np.uint8), bitorder="little")
+        assert np.array_equal(bits.astype(bool), res["blocks"][i] != 2)
+    # vx_frustum_cull: 300 000 chunks x 1000 frames of bytes = 300 MB -> 2 frame slices
+    rng = np.random.default_rng(8)
+    g = np.arange(-274, 274, dtype=np.int32)
+    z, x = np.meshgrid(g, g, indexing="ij")
+    c = np.stack([x.reshape(-1), np.zeros(x.size, np.int32), z.reshape(-1)], 1).astype(np.int32)[:300000]
+    planes = rng.standard_normal((1000, 6, 4)).astype(np.float32)
+    planes[:, :, 3] += 3000.0
+    vis = ctx.frustum_cull(planes, c)
+    assert vis.shape == (1000, 300000)
+    for f in (0, 893, 894, 895, 999):
+        assert np.array_equal(vis[f], oracle.frustum_cull(planes[f:f + 1], c)[0])

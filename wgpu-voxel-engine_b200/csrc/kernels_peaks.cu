@@ -6,7 +6,7 @@
 namespace {
 
 constexpr int kIters = 4096;
-constexpr int kChains = 8;
+constexpr int kChains = 16;
 
 template <int KIND>
 __global__ void __launch_bounds__(256) vx_peak_kernel(float *sink, float seedf, uint32_t seedi)
@@ -18,14 +18,15 @@ __global__ void __launch_bounds__(256) vx_peak_kernel(float *sink, float seedf, 
         a[c] = seedf + (float)(threadIdx.x + c);
         h[c] = seedi + threadIdx.x * 8u + c;
     }
-    const float m = 1.0000001f, b = 1e-7f;
+    const float m = 1.0000001f, b = seedf * 1e-7f;
 #pragma unroll 1
     for (int it = 0; it < kIters; ++it) {
 #pragma unroll
         for (int c = 0; c < kChains; ++c) {
             if (KIND == 0) {
-                a[c] = __fmaf_rn(a[c], m, b);
-                a[c] = __fmaf_rn(a[c], m, b);
+                // immediate multiplicand (the 1-cycle FFMA form) + a register addend
+                a[c] = __fmaf_rn(a[c], 1.0000001f, b);
+                a[c] = __fmaf_rn(a[c], 0.9999999f, b);
             } else if (KIND == 1) {
                 a[c] = __fmul_rn(a[c], m);
                 a[c] = __fadd_rn(a[c], b);

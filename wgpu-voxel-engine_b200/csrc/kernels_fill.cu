@@ -192,6 +192,7 @@ vx_fill_brick_kernel(const vx_fill_args a)
     const float thr1 = a.thr1, thr2 = a.thr2;
 
     const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
+    uint32_t my_word = 0;
 #pragma unroll 1
     for (uint32_t it = 0; it < 16u; ++it) {
         const uint32_t y = 2u * it + yy;
@@ -224,7 +225,13 @@ vx_fill_brick_kernel(const vx_fill_args a)
             solid = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
         }
         const uint32_t word = __ballot_sync(VX_FULL, solid);     // bit = yy*16 + zz*4 + xx
-        if (lane < 8u) nib[2u * it + (lane >> 2)][lane & 3u][xblk] = (uint8_t)((word >> (4u * lane)) & 15u);
+        if (lane == it) my_word = word;                          // lane `it` keeps the word of step `it`
+    }
+    if (lane < 16u) {
+        // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
+#pragma unroll
+        for (uint32_t p8 = 0; p8 < 8u; ++p8)
+            nib[2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
     }
     __syncthreads();
 

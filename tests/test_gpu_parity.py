@@ -510,3 +510,39 @@ def test_host_api_output_slicing(ctx, oracle):
     assert vis.shape == (1000, 300000)
     for f in (0, 893, 894, 895, 999):
         assert np.array_equal(vis[f], oracle.frustum_cull(planes[f:f + 1], c)[0])
+
+
+def test_concurrent_callers_like_the_uvth_pool(ctx, vox):
+    """chunk_builder.rs:80-84 runs Chunk::new / create_mesh on pool threads.  Calls on one context are
+    serialised by the library, separate contexts run side by side; both must give the serial answer."""
+    import threading
+    jobs = [_grid(x0, z0, 3, 3) for x0 in (-9, 0, 9) for z0 in (-9, 0, 9)]
+    serial = [ctx.gen_mesh(j).instances.tobytes() for j in jobs]
+    planes = np.random.default_rng(1).standard_normal((3, 6, 4)).astype(np.float32)
+    serial_vis = [ctx.frustum_cull(planes, j).tobytes() for j in jobs]
+    results, errors = {}, []
+
+    def worker(tid, context, own):
+        try:
+            c = vox.Context() if own else context
+            for rep in range(3):
+                for k, j in enumerate(jobs):
+                    if (k + tid) % 2 == 0:
+                        results[(tid, rep, k, "m")] = c.gen_mesh(j).instances.tobytes()
+                    else:
+                        results[(tid, rep, k, "f")] = c.frustum_cull(planes, j).tobytes()
+                    ch = vox.Chunk.new((k, 0, tid), c)                  # single-chunk calls in between
+                    assert ch.cubes.shape == (32768,)
+            if own:
+                c.close()
+        except Exception as e:                                          # pragma: no cover
+            errors.append(repr(e))
+    threads = [threading.Thread(target=worker, args=(t, ctx, t >= 4)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 8 * 3 * len(jobs)
+    for (tid, rep, k, kind), b in results.items():
+        assert b == (serial[k] if kind == "m" else serial_vis[k]), (tid, rep, k, kind)

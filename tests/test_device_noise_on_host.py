@@ -21,6 +21,9 @@ def shim(tmp_path_factory):
     L.shim_noise_chunk_sign.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.shim_noise_chunk_fused.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.shim_fused_err_ulps.restype = C.c_float
+    L.shim_noise_chunk_lattice.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    for f in (L.shim_noise_chunk_x2, L.shim_noise_chunk_x1):
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
     return L
 
 
@@ -75,3 +78,41 @@ def test_fused_evaluation_stays_inside_its_certified_bound(shim, oracle):
     assert worst <= bound, (worst, bound)
     assert worst > 0                                  # it really is a different rounding sequence
     print("max |fused - exact| = %.3g, certified bound %.3g, kernel margin %.3g" % (worst, bound, 3 * bound))
+
+
+@pytest.mark.parametrize("coord,seed,gain,lac,freq", [((0, 0, 0), 1, 2.5, 0.5, 0.09), ((511, 0, -512), 1, 2.5, 0.5, 0.09),
+                                                       ((9, -3, 4), 77, -3.0, 0.7, 0.2), ((100000, 3, -99999), 5, 1.0, 2.0, 0.03)])
+def test_packed_two_voxel_variant_is_bit_equal_to_the_scalar_fused_one(shim, coord, seed, gain, lac, freq):
+    """vxn_simplex3_fused_x2 (two voxels per thread on FADD2/FMUL2/FFMA2) runs each element through the scalar
+    fused variant's operation sequence: bit-equal, so the certified error bound carries over unchanged."""
+    c = np.array(coord, np.int32)
+    a = np.empty(32768, np.float32)
+    b = np.empty(32768, np.float32)
+    shim.shim_noise_chunk_x2(c.ctypes.data, seed, freq, gain, lac, 1, a.ctypes.data)
+    shim.shim_noise_chunk_x1(c.ctypes.data, seed, freq, gain, lac, 1, b.ctypes.data)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("coord,seed,gain,lac,freq,expect_fit", [
+    ((0, 0, 0), 1, 2.5, 0.5, 0.09, True), ((511, 0, -512), 1, 2.5, 0.5, 0.09, True), ((-1, -1, -1), 1, 2.5, 0.5, 0.09, True),
+    ((9, -3, 4), 77, -3.0, 0.7, 0.1, True), ((100000, 3, -99999), 5, 1.0, 2.0, 0.02, True),
+    ((-200000, 0, 200000), 1, 2.5, 0.5, 0.09, True), ((-30000, 2, 7), 9, 2.5, -0.5, -0.09, True),
+    ((3, 0, 3), 1, 2.5, 0.5, 0.9, False), ((40000000, 0, -40000000), 1, 2.5, 0.5, 0.09, None)])
+def test_lattice_table_variant_is_bit_equal_to_the_scalar_fused_one(shim, coord, seed, gain, lac, freq, expect_fit):
+    """vxn_simplex3_lattice_x2: gradients from a per-CTA table hashed once per lattice point (index box from
+    the 8 box corners) give exactly the per-voxel-hash values; boxes that do not fit are reported, never
+    silently truncated (an unbuilt entry is NaN in this host build)."""
+    c = np.array(coord, np.int32)
+    a = np.full(32768, np.nan, np.float32)
+    b = np.empty(32768, np.float32)
+    unfit = shim.shim_noise_chunk_lattice(c.ctypes.data, seed, freq, gain, lac, a.ctypes.data)
+    shim.shim_noise_chunk_x1(c.ctypes.data, seed, freq, gain, lac, 1, b.ctypes.data)
+    if expect_fit is True:
+        assert unfit == 0
+    elif expect_fit is False:
+        assert unfit == 8
+    got = ~np.isnan(a)
+    zb = (np.arange(32768) // 32 % 32) // 4
+    assert got.reshape(-1).sum() == (8 - unfit) * 4096
+    assert np.array_equal(a.view(np.uint32)[got], b.view(np.uint32)[got])
+    assert len(set(zb[~got])) == unfit

@@ -258,6 +258,320 @@ vx_fill_brick_kernel(const vx_fill_args a)
     }
 }
 
+template <bool WANT_BLOCKS>
+__global__ void __launch_bounds__(256, 2)
+vx_fill_brick2_kernel(const vx_fill_args a)
+{
+    __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
+    // gradient coefficient table (2 KB, one column per lane & 7) placed on a 2048-byte boundary
+    // of the shared window inside a 4 KB buffer
+    __shared__ __align__(16) float4 s_lut_raw[2 * VXN_LUT_FLOAT4S];
+    const uint32_t lut_raw = (uint32_t)__cvta_generic_to_shared(s_lut_raw);
+    const uint32_t lut_base = (lut_raw + 2047u) & ~2047u;
+    float4 *s_lut = s_lut_raw + ((lut_base - lut_raw) >> 4);
+    if (threadIdx.x < VXN_LUT_FLOAT4S) s_lut[threadIdx.x] = vxn_grad_coeffs(threadIdx.x >> 3);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
+    const vxn_lut_ref lut_lane = lut_base + (lane & 7u) * 16u;
+    const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
+    const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
+    const float ox = (float)(int32_t)((uint32_t)cx * 32u);
+    const float oy = (float)(int32_t)((uint32_t)cz * 32u);
+    const float oz = (float)(int32_t)((uint32_t)cy * 32u);
+    const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
+    const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
+    const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const uint32_t seed = (uint32_t)a.p.seed;
+
+    // two voxels per thread: (y, y + 2) of one (x, z) column -> the x / z terms are broadcast pairs
+    float2 hx[3], hy[3], hxy[3];
+    {
+        float fx = __fmul_rn(sx, freq), fy = __fmul_rn(sy, freq);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            if (o) { fx = __fmul_rn(fx, lac); fy = __fmul_rn(fy, lac); }
+            hx[o] = VX2(fx);
+            hy[o] = VX2(fy);
+            hxy[o] = VX2(__fadd_rn(fx, fy));
+        }
+    }
+    const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+    const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
+    const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
+
+    uint32_t my_word = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < 8u; ++it) {
+        // world y of the pair: oz + 4*it + yy (+2); integers below 2^24 in magnitude add exactly, and
+        // beyond that the single rounding of (oz + y) is reproduced by adding the full offset at once
+        const float ya = __fadd_rn(oz, (float)(4u * it + yy)), yb = __fadd_rn(oz, (float)(4u * it + yy + 2u));
+        // scalar multiplies: ptxas would contract a packed product into the packed adds that consume z
+        const float za0 = __fmul_rn(ya, freq), zb0 = __fmul_rn(yb, freq);
+        const float za1 = __fmul_rn(za0, lac), zb1 = __fmul_rn(zb0, lac);
+        const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
+        // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
+        bool solid_a, solid_b, certain;
+        const float2 u = __fmul2_rn(vxn_simplex3_fused_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], seed, lut_lane), VX2(amp2));
+        if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
+            solid_a = u.x < 0.0f;
+            solid_b = u.y < 0.0f;
+            certain = true;
+        } else {
+            const float2 ut = __ffma2_rn(vxn_simplex3_fused_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], seed, lut_lane), VX2(amp1), u);
+            if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
+                solid_a = ut.x < 0.0f;
+                solid_b = ut.y < 0.0f;
+                certain = true;
+            } else {
+                const float2 r = __fadd2_rn(ut, vxn_simplex3_fused_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], seed, lut_lane));
+                solid_a = r.x < 0.0f;
+                solid_b = r.y < 0.0f;
+                certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;
+            }
+        }
+        if (__any_sync(VX_FULL, !certain)) {
+            // some voxel is within the margin of zero: redo the step on the scalar path with the
+            // reference's exact operation order (separately rounded, r = u + (t + s1))
+#pragma unroll 1
+            for (int e = 0; e < 2; ++e) {
+                const float q0 = e ? zb0 : za0, q1 = e ? zb1 : za1, q2 = e ? zb2 : za2;
+                const float ue = __fmul_rn(vxn_simplex3_sign<false>(hx[2].x, hy[2].x, q2, hxy[2].x, seed, lut_lane), amp2);
+                const float te = __fmul_rn(vxn_simplex3_sign<false>(hx[1].x, hy[1].x, q1, hxy[1].x, seed, lut_lane), amp1);
+                const float s1 = vxn_simplex3_sign<false>(hx[0].x, hy[0].x, q0, hxy[0].x, seed, lut_lane);
+                const bool sol = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
+                if (e) solid_b = sol; else solid_a = sol;
+            }
+        }
+        // words of the old 2-row steps 2*it (y = 4 it + yy) and 2*it + 1 (y = 4 it + 2 + yy); bit = yy*16 + zz*4 + xx
+        const uint32_t word_a = __ballot_sync(VX_FULL, solid_a), word_b = __ballot_sync(VX_FULL, solid_b);
+        if (lane == 2u * it) my_word = word_a;
+        if (lane == 2u * it + 1u) my_word = word_b;
+    }
+    if (lane < 16u) {
+        // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
+#pragma unroll
+        for (uint32_t p8 = 0; p8 < 8u; ++p8)
+            nib[2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
+    }
+    __syncthreads();
+
+    // 128 row words of this z block: row (y, zblk*4 + zz) = 8 nibbles, one per x block
+    const uint32_t t = threadIdx.x;
+    const uint32_t rr = t >> 1, half = t & 1u;                  // row 0..127, 16-voxel half
+    const uint32_t y = rr >> 2, zq = rr & 3u;
+    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[y][zq][0]);
+    // pack the low nibble of each of the 8 bytes into one 32-bit word
+    const uint32_t lo = (nb.x & 0x0f0f0f0fu), hi = (nb.y & 0x0f0f0f0fu);
+    const uint32_t plo = (lo | (lo >> 4)) & 0x00ff00ffu, phi = (hi | (hi >> 4)) & 0x00ff00ffu;
+    const uint32_t w16lo = (plo | (plo >> 8)) & 0xffffu, w16hi = (phi | (phi >> 8)) & 0xffffu;
+    const uint32_t wordv = w16lo | (w16hi << 16);
+    if (half == 0) a.occ[(size_t)item * VX_ROWS + y * 32u + zblk * 4u + zq] = wordv;
+    if (WANT_BLOCKS) {
+        const uint32_t air16 = ~(wordv >> (16u * half)) & 0xffffu;
+        uint4 v;
+        v.x = (((air16 >> 0) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.y = (((air16 >> 4) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.z = (((air16 >> 8) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        *reinterpret_cast<uint4 *>(a.blocks + (size_t)item * VX_VOXELS + (size_t)y * 1024u +
+                                   (zblk * 4u + zq) * 32u + half * 16u) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Lattice-table fast path (vx_noise.cuh "Lattice-table gradients"): same CTA / warp / lane layout
+// and the same sign-only octave skipping as vx_fill_brick2_kernel, but the corner gradients come
+// from a per-CTA shared-memory table hashed once per lattice point instead of once per voxel corner.
+// A CTA whose index box does not fit the table runs the table-free exact evaluation (rare: huge
+// frequencies or coordinates beyond f32 resolution).
+// ---------------------------------------------------------------------------
+__device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float oz, uint32_t yy, uint32_t lane,
+                                                      float freq, float lac, float gain, uint32_t seed)
+{
+    const float x0 = __fmul_rn(sx, freq), y0 = __fmul_rn(sy, freq);
+    const float x1 = __fmul_rn(x0, lac), y1 = __fmul_rn(y0, lac);
+    const float x2 = __fmul_rn(x1, lac), y2 = __fmul_rn(y1, lac);
+    const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+    uint32_t my_word = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < 16u; ++it) {
+        const float z0 = __fmul_rn(__fadd_rn(oz, (float)(2u * it + yy)), freq);
+        const float z1 = __fmul_rn(z0, lac), z2 = __fmul_rn(z1, lac);
+        float r = vxn_simplex3(x0, y0, z0, __fadd_rn(x0, y0), seed);
+        r = __fadd_rn(__fmul_rn(vxn_simplex3(x1, y1, z1, __fadd_rn(x1, y1), seed), amp1), r);
+        r = __fadd_rn(__fmul_rn(vxn_simplex3(x2, y2, z2, __fadd_rn(x2, y2), seed), amp2), r);
+        const uint32_t word = __ballot_sync(VX_FULL, r < 0.0f);
+        if (lane == it) my_word = word;
+    }
+    return my_word;
+}
+
+template <bool WANT_BLOCKS>
+__global__ void __launch_bounds__(256, 2)
+vx_fill_lattice_kernel(const vx_fill_args a)
+{
+    __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
+    __shared__ __align__(16) unsigned char s_tab[3][VXL_TAB_BYTES];
+    __shared__ int32_t s_box[3][6];                       // per octave: min i, j, k, max i, j, k
+    const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
+    const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
+    const float ox = (float)(int32_t)((uint32_t)cx * 32u);
+    const float oy = (float)(int32_t)((uint32_t)cz * 32u);
+    const float oz = (float)(int32_t)((uint32_t)cy * 32u);
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const uint32_t seed = (uint32_t)a.p.seed;
+
+    // ---- index box of this CTA's 32 x 4 x 32 voxels, per octave: floor indices at the 8 corners
+    if (threadIdx.x < 32u) {
+        const uint32_t o = min(lane >> 3, 2u), c = lane & 7u;
+        float fx = __fmul_rn(__fadd_rn(ox, (c & 1u) ? 31.0f : 0.0f), freq);
+        float fy = __fmul_rn(__fadd_rn(oy, (float)(zblk * 4u + ((c & 2u) ? 3u : 0u))), freq);
+        float fz = __fmul_rn(__fadd_rn(oz, (c & 4u) ? 31.0f : 0.0f), freq);
+#pragma unroll
+        for (uint32_t q = 0; q < 2u; ++q)
+            if (q < o) { fx = __fmul_rn(fx, lac); fy = __fmul_rn(fy, lac); fz = __fmul_rn(fz, lac); }
+        int32_t lo[3], hi[3];
+        vxl_cell_index(fx, fy, fz, __fadd_rn(fx, fy), &lo[0], &lo[1], &lo[2]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            hi[d] = lo[d];
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                lo[d] = min(lo[d], __shfl_xor_sync(VX_FULL, lo[d], m));
+                hi[d] = max(hi[d], __shfl_xor_sync(VX_FULL, hi[d], m));
+            }
+        }
+        if (c == 0u && lane < 24u) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { s_box[o][d] = lo[d]; s_box[o][3 + d] = hi[d]; }
+        }
+    }
+    __syncthreads();
+    bool fit = true;
+    uint32_t org[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const uint32_t ni = (uint32_t)(s_box[o][3] - s_box[o][0]), nj = (uint32_t)(s_box[o][4] - s_box[o][1]),
+                       nk = (uint32_t)(s_box[o][5] - s_box[o][2]);
+        fit = fit && ni <= VXL_DIM - 2u && nj <= VXL_DIM - 2u && nk <= VXL_DIM - 2u;
+        org[o] = (uint32_t)__cvta_generic_to_shared(&s_tab[o][0]) -
+                 ((uint32_t)s_box[o][0] * VXL_SI + (uint32_t)s_box[o][1] * VXL_SJ + (uint32_t)s_box[o][2] * VXL_SK);
+    }
+    const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
+    const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
+    const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
+    uint32_t my_word = 0;
+    if (!fit) {
+        my_word = vx_brick_exact_steps(sx, sy, oz, yy, lane, freq, lac, gain, seed);
+    } else {
+        // ---- hash every lattice point of the three boxes once (+1 per axis for the far corners)
+#pragma unroll 1
+        for (int o = 0; o < 3; ++o) {
+            const int32_t i0 = s_box[o][0], j0 = s_box[o][1], k0 = s_box[o][2];
+            const uint32_t ni = (uint32_t)(s_box[o][3] - i0) + 2u, nj = (uint32_t)(s_box[o][4] - j0) + 2u,
+                           nk = (uint32_t)(s_box[o][5] - k0) + 2u;
+            for (uint32_t e = threadIdx.x; e < ni * 64u; e += 256u) {
+                const uint32_t ea = e >> 6, eb = (e >> 3) & 7u, ec = e & 7u;
+                if (eb < nj && ec < nk)
+                    *reinterpret_cast<float4 *>(&s_tab[o][ea * VXL_SI + eb * VXL_SJ + ec * VXL_SK]) =
+                        vxl_entry(seed, i0 + (int32_t)ea, j0 + (int32_t)eb, k0 + (int32_t)ec);
+            }
+        }
+        __syncthreads();
+
+        // two voxels per thread: (y, y + 2) of one (x, z) column -> the x / z terms are broadcast pairs
+        float2 hx[3], hy[3], hxy[3];
+        {
+            float fx = __fmul_rn(sx, freq), fy = __fmul_rn(sy, freq);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                if (o) { fx = __fmul_rn(fx, lac); fy = __fmul_rn(fy, lac); }
+                hx[o] = VX2(fx);
+                hy[o] = VX2(fy);
+                hxy[o] = VX2(__fadd_rn(fx, fy));
+            }
+        }
+        const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+        const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
+        const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
+#pragma unroll 1
+        for (uint32_t it = 0; it < 8u; ++it) {
+            const float ya = __fadd_rn(oz, (float)(4u * it + yy)), yb = __fadd_rn(oz, (float)(4u * it + yy + 2u));
+            // scalar multiplies: ptxas would contract a packed product into the packed adds that consume z
+            const float za0 = __fmul_rn(ya, freq), zb0 = __fmul_rn(yb, freq);
+            const float za1 = __fmul_rn(za0, lac), zb1 = __fmul_rn(zb0, lac);
+            const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
+            // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
+            bool solid_a, solid_b, certain;
+            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], org[2], 0), VX2(amp2));
+            if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
+                solid_a = u.x < 0.0f;
+                solid_b = u.y < 0.0f;
+                certain = true;
+            } else {
+                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], org[1], 0), VX2(amp1), u);
+                if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
+                    solid_a = ut.x < 0.0f;
+                    solid_b = ut.y < 0.0f;
+                    certain = true;
+                } else {
+                    const float2 r = __fadd2_rn(ut, vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], org[0], 0));
+                    solid_a = r.x < 0.0f;
+                    solid_b = r.y < 0.0f;
+                    certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;
+                }
+            }
+            if (__any_sync(VX_FULL, !certain)) {
+                // some voxel is within the margin of zero: redo the step with the exact scalar noise in
+                // the reference's operation order (separately rounded, r = u + (t + s1))
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) {
+                    const float q0 = e ? zb0 : za0, q1 = e ? zb1 : za1, q2 = e ? zb2 : za2;
+                    const float ue = __fmul_rn(vxn_simplex3(hx[2].x, hy[2].x, q2, hxy[2].x, seed), amp2);
+                    const float te = __fmul_rn(vxn_simplex3(hx[1].x, hy[1].x, q1, hxy[1].x, seed), amp1);
+                    const float s1 = vxn_simplex3(hx[0].x, hy[0].x, q0, hxy[0].x, seed);
+                    const bool sol = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
+                    if (e) solid_b = sol; else solid_a = sol;
+                }
+            }
+            // words of the 2-row steps 2*it (y = 4 it + yy) and 2*it + 1 (y = 4 it + 2 + yy); bit = yy*16 + zz*4 + xx
+            const uint32_t word_a = __ballot_sync(VX_FULL, solid_a), word_b = __ballot_sync(VX_FULL, solid_b);
+            if (lane == 2u * it) my_word = word_a;
+            if (lane == 2u * it + 1u) my_word = word_b;
+        }
+    }
+    if (lane < 16u) {
+        // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
+#pragma unroll
+        for (uint32_t p8 = 0; p8 < 8u; ++p8)
+            nib[2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
+    }
+    __syncthreads();
+
+    // 128 row words of this z block: row (y, zblk*4 + zz) = 8 nibbles, one per x block
+    const uint32_t t = threadIdx.x;
+    const uint32_t rr = t >> 1, half = t & 1u;                  // row 0..127, 16-voxel half
+    const uint32_t y = rr >> 2, zq = rr & 3u;
+    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[y][zq][0]);
+    const uint32_t lo = (nb.x & 0x0f0f0f0fu), hi = (nb.y & 0x0f0f0f0fu);
+    const uint32_t plo = (lo | (lo >> 4)) & 0x00ff00ffu, phi = (hi | (hi >> 4)) & 0x00ff00ffu;
+    const uint32_t w16lo = (plo | (plo >> 8)) & 0xffffu, w16hi = (phi | (phi >> 8)) & 0xffffu;
+    const uint32_t wordv = w16lo | (w16hi << 16);
+    if (half == 0) a.occ[(size_t)item * VX_ROWS + y * 32u + zblk * 4u + zq] = wordv;
+    if (WANT_BLOCKS) {
+        const uint32_t air16 = ~(wordv >> (16u * half)) & 0xffffu;
+        uint4 v;
+        v.x = (((air16 >> 0) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.y = (((air16 >> 4) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.z = (((air16 >> 8) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
+        *reinterpret_cast<uint4 *>(a.blocks + (size_t)item * VX_VOXELS + (size_t)y * 1024u +
+                                   (zblk * 4u + zq) * 32u + half * 16u) = v;
+    }
+}
+
 template <int OCT, bool HALO>
 cudaError_t launch_oct(const vx_fill_args &a, cudaStream_t s)
 {
@@ -310,8 +624,17 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
         // octave amplitudes, plus the roundings of the FBM combination; x3 slack on top.
         b.err_margin = 3.0f * (VXN_FUSED_ERR_ULPS * (1.0f + g1 + g2) + 2.0f * (1.0f + g1 + g2)) * 5.9604645e-8f;
         const uint32_t n_items = a.max_units / 32u;
-        if (a.blocks) vx_fill_brick_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
-        else vx_fill_brick_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);
+        // lattice tables hold 8 points per axis: a 32-voxel edge spans <= 52.7 * |f_k| cells in the skewed
+        // index (x + (x + y + z) / 3), so |f_k| <= 0.1 fits with room for rounding; CTAs that still do
+        // not fit (f32 spacing at huge coordinates) take their in-kernel exact path
+        const float f0 = fabsf(a.p.freq), f1 = f0 * fabsf(a.p.lacunarity), f2 = f1 * fabsf(a.p.lacunarity);
+        if (fmaxf(f0, fmaxf(f1, f2)) <= 0.1f) {
+            if (a.blocks) vx_fill_lattice_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
+            else vx_fill_lattice_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);
+        } else {
+            if (a.blocks) vx_fill_brick2_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
+            else vx_fill_brick2_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);
+        }
         return cudaGetLastError();
     }
     // octaves = 3 otherwise gets the fully hoisted exact instantiation;

@@ -208,3 +208,212 @@ __device__ __forceinline__ float vxn_simplex3_sign(float x, float y, float z, fl
     const float v0 = __fmul_rn(w0, g0), v1 = __fmul_rn(w1, g1), v2 = __fmul_rn(w2, g2), v3 = __fmul_rn(w3, g3);
     return __fadd_rn(__fadd_rn(__fadd_rn(v3, v2), v1), v0);
 }
+
+// ---------------------------------------------------------------------------
+// Two voxels per thread on the packed FP32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2 operate on
+// an aligned register pair and take ONE issue slot for two IEEE-rn results).  The fill kernel is
+// issue-bound, and 55 of the 67 FP operations of one simplex evaluation pack.  Only the FUSED
+// (certified-margin) evaluation exists in this form; element k of every pair goes through exactly
+// the operation sequence of vxn_simplex3_sign<true> on voxel k (a - b is written a + (-b), the
+// max(t, 0) clamp is the .SAT modifier of the last scalar op of t, t <= 0.6 < 1), so values and
+// the certified error bound are unchanged bit for bit (tests/test_device_noise_on_host.py).
+//
+// ptxas 12.9 CONTRACTS mul.rn.f32x2 + add.rn.f32x2 INTO FFMA2 even under --fmad=false (it honours
+// the explicit .rn only for scalar f32).  The cell selection must be the reference's separately
+// rounded sequence, so every product that feeds an add there (f = F3 * s, g = G3 * t, and the
+// caller's z = y * freq * lac^k) is a SCALAR __fmul_rn -- ptxas does not fuse across the scalar /
+// packed boundary -- and the exact fallback of the kernel stays on the scalar vxn_simplex3_sign<false>.
+// In the smooth part below no packed product feeds a packed add except through explicit fma.
+// What else stays scalar: floor / float->int, the hashes, the corner selects and the gradient dots
+// (their coefficients arrive by LDS.128 as 4 consecutive registers, not as cross-voxel pairs).
+// ---------------------------------------------------------------------------
+#define VX2(c) make_float2((c), (c))
+__device__ __forceinline__ float2 vx2_neg(float2 a) { return make_float2(-a.x, -a.y); }
+// scalar * pair with two scalar multiplies (never contractible into a following packed add)
+__device__ __forceinline__ float2 vx2_scale_unfused(float c, float2 a) { return make_float2(__fmul_rn(c, a.x), __fmul_rn(c, a.y)); }
+
+__device__ __forceinline__ float2 vxn_weight_x2(float2 a, float2 b, float2 c)
+{
+    const float2 s = __ffma2_rn(vx2_neg(b), b, __ffma2_rn(vx2_neg(a), a, VX2(0.6f)));
+    float2 t = make_float2(__saturatef(__fmaf_rn(-c.x, c.x, s.x)), __saturatef(__fmaf_rn(-c.y, c.y, s.y)));
+    t = __fmul2_rn(t, t);
+    return __fmul2_rn(t, t);
+}
+
+// z must come from scalar multiplies (see above); x, y, xy are usually broadcast pairs.
+__device__ __forceinline__ float2 vxn_simplex3_fused_x2(float2 x, float2 y, float2 z, float2 xy, uint32_t seed,
+                                                        vxn_lut_ref lut_lane)
+{
+    // ---- cell selection: the reference's exact operation sequence per element ------------------
+    const float2 f = vx2_scale_unfused(VXN_F3, __fadd2_rn(xy, z));
+    const float2 xs = __fadd2_rn(x, f), ys = __fadd2_rn(y, f), zs = __fadd2_rn(z, f);
+    const float2 xf = make_float2(floorf(xs.x), floorf(xs.y));
+    const float2 yf = make_float2(floorf(ys.x), floorf(ys.y));
+    const float2 zf = make_float2(floorf(zs.x), floorf(zs.y));
+
+    const float2 g = vx2_scale_unfused(VXN_G3, __fadd2_rn(__fadd2_rn(xf, yf), zf));
+    const float2 x0 = __fadd2_rn(x, vx2_neg(__fadd2_rn(xf, vx2_neg(g))));
+    const float2 y0 = __fadd2_rn(y, vx2_neg(__fadd2_rn(yf, vx2_neg(g))));
+    const float2 z0 = __fadd2_rn(z, vx2_neg(__fadd2_rn(zf, vx2_neg(g))));
+    const float2 xm = __fadd2_rn(x0, VX2(-1.0f)), ym = __fadd2_rn(y0, VX2(-1.0f)), zm = __fadd2_rn(z0, VX2(-1.0f));
+    const float2 x3 = __fadd2_rn(x0, VX2(VXN_G33)), y3 = __fadd2_rn(y0, VX2(VXN_G33)), z3 = __fadd2_rn(z0, VX2(VXN_G33));
+
+    // per element: lattice hashes of the four corners and the pre-add operands of corners 1 and 2
+    uint32_t h0[2], h1[2], h2[2], h3[2];
+    float sx1[2], sy1[2], sz1[2], sx2[2], sy2[2], sz2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float ex0 = e ? x0.y : x0.x, ey0 = e ? y0.y : y0.x, ez0 = e ? z0.y : z0.x;
+        const float exm = e ? xm.y : xm.x, eym = e ? ym.y : ym.x, ezm = e ? zm.y : zm.x;
+        const uint32_t ib0 = (uint32_t)__float2int_rz(e ? xf.y : xf.x) * VXN_XP;
+        const uint32_t ia = ib0 ^ seed, ib = (ib0 + VXN_XP) ^ seed;
+        const uint32_t ja = (uint32_t)__float2int_rz(e ? yf.y : yf.x) * VXN_YP, jb = ja + VXN_YP;
+        const uint32_t ka = (uint32_t)__float2int_rz(e ? zf.y : zf.x) * VXN_ZP, kb = ka + VXN_ZP;
+        const bool xy_ = ex0 >= ey0, yz_ = ey0 >= ez0, xz_ = ex0 >= ez0;
+        const bool i1 = xy_ && xz_, j1 = !xy_ && yz_, k1 = !xz_ && !yz_;
+        const bool i2 = xy_ || xz_, j2 = !xy_ || yz_, k2 = !(xz_ && yz_);
+        sx1[e] = i1 ? exm : ex0; sy1[e] = j1 ? eym : ey0; sz1[e] = k1 ? ezm : ez0;
+        sx2[e] = i2 ? exm : ex0; sy2[e] = j2 ? eym : ey0; sz2[e] = k2 ? ezm : ez0;
+        h0[e] = ia ^ ja ^ ka;
+        h1[e] = (i1 ? ib : ia) ^ (j1 ? jb : ja) ^ (k1 ? kb : ka);
+        h2[e] = (i2 ? ib : ia) ^ (j2 ? jb : ja) ^ (k2 ? kb : ka);
+        h3[e] = ib ^ jb ^ kb;
+    }
+    const float2 x1 = __fadd2_rn(make_float2(sx1[0], sx1[1]), VX2(VXN_G3));
+    const float2 y1 = __fadd2_rn(make_float2(sy1[0], sy1[1]), VX2(VXN_G3));
+    const float2 z1 = __fadd2_rn(make_float2(sz1[0], sz1[1]), VX2(VXN_G3));
+    const float2 x2 = __fadd2_rn(make_float2(sx2[0], sx2[1]), VX2(VXN_F3));
+    const float2 y2 = __fadd2_rn(make_float2(sy2[0], sy2[1]), VX2(VXN_F3));
+    const float2 z2 = __fadd2_rn(make_float2(sz2[0], sz2[1]), VX2(VXN_F3));
+    // gradient dots: scalar (coefficients come from LDS.128, one table row per element)
+    const float2 g0 = make_float2(vxn_grad_lut<true>(h0[0], x0.x, y0.x, z0.x, lut_lane),
+                                  vxn_grad_lut<true>(h0[1], x0.y, y0.y, z0.y, lut_lane));
+    const float2 g1 = make_float2(vxn_grad_lut<true>(h1[0], x1.x, y1.x, z1.x, lut_lane),
+                                  vxn_grad_lut<true>(h1[1], x1.y, y1.y, z1.y, lut_lane));
+    const float2 g2 = make_float2(vxn_grad_lut<true>(h2[0], x2.x, y2.x, z2.x, lut_lane),
+                                  vxn_grad_lut<true>(h2[1], x2.y, y2.y, z2.y, lut_lane));
+    const float2 g3 = make_float2(vxn_grad_lut<true>(h3[0], x3.x, y3.x, z3.x, lut_lane),
+                                  vxn_grad_lut<true>(h3[1], x3.y, y3.y, z3.y, lut_lane));
+    // ---- smooth part ---------------------------------------------------------------------------
+    const float2 w0 = vxn_weight_x2(x0, y0, z0), w1 = vxn_weight_x2(x1, y1, z1);
+    const float2 w2 = vxn_weight_x2(x2, y2, z2), w3 = vxn_weight_x2(x3, y3, z3);
+    return __ffma2_rn(w0, g0, __ffma2_rn(w1, g1, __ffma2_rn(w2, g2, __fmul2_rn(w3, g3))));
+}
+
+// ---------------------------------------------------------------------------
+// Lattice-table gradients.  The hash of a simplex corner depends only on the integer lattice point
+// (i, j, k), and one fill CTA (32 x 4 x 32 voxels) touches at most a few hundred lattice points per
+// octave (freq 0.09: 7 x 5 x 7; the lower octaves fewer).  The CTA hashes every lattice point of its
+// index box ONCE into a shared-memory table of gradient coefficients; a corner then costs one
+// LDS.128 at   org + i*SI + j*SJ + k*SK   instead of 3 IMAD + 3 LOP3 + 2 SHF + LDS  (the per-voxel
+// hashing was ~45 % of the issue slots and ~55 % of the ALU-pipe work of one evaluation).
+// Corner offsets are immediates: corner 1 adds the stride of the largest coordinate, corner 2 the
+// strides of the two largest, corner 3 all three.  SI / SJ are padded (75 / 9 entries) so lattice
+// neighbours fall into different 16-byte bank groups.
+//
+// The index box is exact, not estimated: every step of the cell selection is a monotone function of
+// each voxel index (IEEE rounding is monotone), so the floor indices over a voxel box are bounded by
+// their values at the 8 box corners, which the CTA evaluates with the very same operation sequence.
+// A box that does not fit VXL_DIM entries per axis (huge freq, or |coords| where f32 spacing exceeds
+// the cell size) makes the CTA take the table-free exact path instead.
+// ---------------------------------------------------------------------------
+#define VXL_DIM 8u                       /* lattice points per axis a table can hold */
+#define VXL_SK 16u                       /* byte strides: k, j (9 entries), i (75 entries) */
+#define VXL_SJ 144u
+#define VXL_SI 1200u
+#define VXL_S3 (VXL_SI + VXL_SJ + VXL_SK)
+#define VXL_TAB_BYTES 9600u              /* >= 7*SI + 7*SJ + 7*SK + 16 */
+
+#if defined(__CUDACC__)
+typedef uint32_t vxl_tab_ref;            // device: the shared-window base is folded into `org`; pass 0
+__device__ __forceinline__ float4 vxl_load(vxl_tab_ref, uint32_t addr)
+{
+    float4 c;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(addr));
+    return c;
+}
+#else
+typedef const char *vxl_tab_ref;         // host build: base pointer, `org` is a plain byte offset
+static inline float4 vxl_load(vxl_tab_ref tab, uint32_t off) { float4 c; memcpy(&c, tab + off, 16); return c; }
+#endif
+
+// gradient coefficients of lattice point (i, j, k): same hash as vxn_grad / vxn_grad_lut
+__device__ __forceinline__ float4 vxl_entry(uint32_t seed, int32_t i, int32_t j, int32_t k)
+{
+    uint32_t h = (((uint32_t)i * VXN_XP) ^ seed) ^ ((uint32_t)j * VXN_YP) ^ ((uint32_t)k * VXN_ZP);
+    h = ((h * h) * 60493u) * h;
+    return vxn_grad_coeffs(((h >> 13) ^ h) & 15u);
+}
+
+// floor indices of one voxel: the cell selection's own sequence (used for the box corners)
+__device__ __forceinline__ void vxl_cell_index(float x, float y, float z, float xy, int32_t *i, int32_t *j, int32_t *k)
+{
+    const float f = __fmul_rn(VXN_F3, __fadd_rn(xy, z));
+    *i = __float2int_rz(floorf(__fadd_rn(x, f)));
+    *j = __float2int_rz(floorf(__fadd_rn(y, f)));
+    *k = __float2int_rz(floorf(__fadd_rn(z, f)));
+}
+
+// org = (table base) - (i0*SI + j0*SJ + k0*SK) mod 2^32, (i0, j0, k0) the box minimum.
+__device__ __forceinline__ float2 vxn_simplex3_lattice_x2(float2 x, float2 y, float2 z, float2 xy, uint32_t org,
+                                                          vxl_tab_ref tab)
+{
+    // ---- cell selection: the reference's exact operation sequence per element ------------------
+    const float2 f = vx2_scale_unfused(VXN_F3, __fadd2_rn(xy, z));
+    const float2 xs = __fadd2_rn(x, f), ys = __fadd2_rn(y, f), zs = __fadd2_rn(z, f);
+    const float2 xf = make_float2(floorf(xs.x), floorf(xs.y));
+    const float2 yf = make_float2(floorf(ys.x), floorf(ys.y));
+    const float2 zf = make_float2(floorf(zs.x), floorf(zs.y));
+
+    const float2 g = vx2_scale_unfused(VXN_G3, __fadd2_rn(__fadd2_rn(xf, yf), zf));
+    const float2 x0 = __fadd2_rn(x, vx2_neg(__fadd2_rn(xf, vx2_neg(g))));
+    const float2 y0 = __fadd2_rn(y, vx2_neg(__fadd2_rn(yf, vx2_neg(g))));
+    const float2 z0 = __fadd2_rn(z, vx2_neg(__fadd2_rn(zf, vx2_neg(g))));
+    const float2 xm = __fadd2_rn(x0, VX2(-1.0f)), ym = __fadd2_rn(y0, VX2(-1.0f)), zm = __fadd2_rn(z0, VX2(-1.0f));
+    const float2 x3 = __fadd2_rn(x0, VX2(VXN_G33)), y3 = __fadd2_rn(y0, VX2(VXN_G33)), z3 = __fadd2_rn(z0, VX2(VXN_G33));
+
+    uint32_t a0[2], a1[2], a2[2];
+    float sx1[2], sy1[2], sz1[2], sx2[2], sy2[2], sz2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float ex0 = e ? x0.y : x0.x, ey0 = e ? y0.y : y0.x, ez0 = e ? z0.y : z0.x;
+        const float exm = e ? xm.y : xm.x, eym = e ? ym.y : ym.x, ezm = e ? zm.y : zm.x;
+        const uint32_t xi = (uint32_t)__float2int_rz(e ? xf.y : xf.x);
+        const uint32_t yj = (uint32_t)__float2int_rz(e ? yf.y : yf.x);
+        const uint32_t zk = (uint32_t)__float2int_rz(e ? zf.y : zf.x);
+        const uint32_t base = xi * VXL_SI + (yj * VXL_SJ + (zk * VXL_SK + org));
+        const bool xy_ = ex0 >= ey0, yz_ = ey0 >= ez0, xz_ = ex0 >= ez0;
+        const bool i1 = xy_ && xz_, j1 = !xy_ && yz_, k1 = !xz_ && !yz_;
+        const bool i2 = xy_ || xz_, j2 = !xy_ || yz_, k2 = !(xz_ && yz_);
+        sx1[e] = i1 ? exm : ex0; sy1[e] = j1 ? eym : ey0; sz1[e] = k1 ? ezm : ez0;
+        sx2[e] = i2 ? exm : ex0; sy2[e] = j2 ? eym : ey0; sz2[e] = k2 ? ezm : ez0;
+        // exactly one of (i1, j1, k1) is set and exactly one of (i2, j2, k2) is clear (a total order)
+        a0[e] = base;
+        a1[e] = base + (i1 ? VXL_SI : (j1 ? VXL_SJ : VXL_SK));
+        a2[e] = base + (VXL_S3 - (!i2 ? VXL_SI : (!j2 ? VXL_SJ : VXL_SK)));
+    }
+    const float2 x1 = __fadd2_rn(make_float2(sx1[0], sx1[1]), VX2(VXN_G3));
+    const float2 y1 = __fadd2_rn(make_float2(sy1[0], sy1[1]), VX2(VXN_G3));
+    const float2 z1 = __fadd2_rn(make_float2(sz1[0], sz1[1]), VX2(VXN_G3));
+    const float2 x2 = __fadd2_rn(make_float2(sx2[0], sx2[1]), VX2(VXN_F3));
+    const float2 y2 = __fadd2_rn(make_float2(sy2[0], sy2[1]), VX2(VXN_F3));
+    const float2 z2 = __fadd2_rn(make_float2(sz2[0], sz2[1]), VX2(VXN_F3));
+    float2 g0, g1, g2, g3;
+    {
+        const float4 c00 = vxl_load(tab, a0[0]), c01 = vxl_load(tab, a0[1]);
+        const float4 c10 = vxl_load(tab, a1[0]), c11 = vxl_load(tab, a1[1]);
+        const float4 c20 = vxl_load(tab, a2[0]), c21 = vxl_load(tab, a2[1]);
+        const float4 c30 = vxl_load(tab, a0[0] + VXL_S3), c31 = vxl_load(tab, a0[1] + VXL_S3);
+        g0 = make_float2(__fmaf_rn(c00.z, z0.x, __fmaf_rn(c00.y, y0.x, __fmul_rn(c00.x, x0.x))),
+                         __fmaf_rn(c01.z, z0.y, __fmaf_rn(c01.y, y0.y, __fmul_rn(c01.x, x0.y))));
+        g1 = make_float2(__fmaf_rn(c10.z, z1.x, __fmaf_rn(c10.y, y1.x, __fmul_rn(c10.x, x1.x))),
+                         __fmaf_rn(c11.z, z1.y, __fmaf_rn(c11.y, y1.y, __fmul_rn(c11.x, x1.y))));
+        g2 = make_float2(__fmaf_rn(c20.z, z2.x, __fmaf_rn(c20.y, y2.x, __fmul_rn(c20.x, x2.x))),
+                         __fmaf_rn(c21.z, z2.y, __fmaf_rn(c21.y, y2.y, __fmul_rn(c21.x, x2.y))));
+        g3 = make_float2(__fmaf_rn(c30.z, z3.x, __fmaf_rn(c30.y, y3.x, __fmul_rn(c30.x, x3.x))),
+                         __fmaf_rn(c31.z, z3.y, __fmaf_rn(c31.y, y3.y, __fmul_rn(c31.x, x3.y))));
+    }
+    const float2 w0 = vxn_weight_x2(x0, y0, z0), w1 = vxn_weight_x2(x1, y1, z1);
+    const float2 w2 = vxn_weight_x2(x2, y2, z2), w3 = vxn_weight_x2(x3, y3, z3);
+    return __ffma2_rn(w0, g0, __ffma2_rn(w1, g1, __ffma2_rn(w2, g2, __fmul2_rn(w3, g3))));
+}

@@ -408,7 +408,8 @@ __device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float 
 }
 
 template <bool WANT_BLOCKS>
-__global__ void __launch_bounds__(256, 2)
+// 64 registers -> 4 CTAs (32 warps) per SM: measured 0.326 / 0.301 / 0.288 ms at 2 / 3 / 4 CTAs per SM
+__global__ void __launch_bounds__(256, 4)
 vx_fill_lattice_kernel(const vx_fill_args a)
 {
     __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits

@@ -362,13 +362,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {
-            "kernel": "vx_fill_kernel (noise fill, FP32 ALU + INT32; not HBM- or tensor-bound)",
+            "kernel": "vx_fill_lattice_kernel (noise fill: FP32 + INT32 instruction issue; not HBM- or tensor-bound)",
             "bound": "fp32", "achieved": fill_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
             "frac": (fill_tflops / ffma_peak) if fill_tflops and ffma_peak else None,
             "peak_source": "FP32 FFMA peak measured live by vx_measure_peak (MEASURED_PEAKS.json has no FP32 figure)",
             "peak_nonfused": nofuse_peak,
             "frac_nonfused": (fill_tflops / nofuse_peak) if fill_tflops and nofuse_peak else None,
-            "note": "bit-exact noise may not contract a*b+c, so the FMUL+FADD peak is the reachable ceiling",
+            "note": "achieved = the reference algorithm's flops (3 octaves x 78 per voxel) / fill time; the kernel skips "
+                    "octaves that cannot flip the sign, so it executes fewer; the cell selection may not contract "
+                    "a*b+c (bit-exact), the smooth part uses FMA under a certified error margin",
             "flop_per_voxel": FLOP_PER_VOXEL, "voxels_per_launch": n * VOXELS, "ms_per_launch": fill_ms,
             "traffic": traffic.get("fill"),
         },

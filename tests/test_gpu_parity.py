@@ -230,6 +230,14 @@ def test_fill_sign_only_shortcuts_are_exact(ctx, vox):
         b = ctx.fill(far, params=p, blocks=True, noise=True)
         assert np.array_equal(a, b["blocks"]), (gain, lac, freq, seed)
         assert np.array_equal(a == 0, b["noise"] < 0)
+    # coordinates where the f32 spacing of the noise coordinate reaches the simplex cell size: some CTAs of
+    # the lattice-table kernel no longer fit their index box and take the in-kernel exact path
+    huge = np.array([(40000000, 0, -40000000), (3000000, 1, 3000000), (20000000, -5, 123), (-1500000, 0, 900000),
+                     (6000000, 2, -6000001), (66000000, 0, 66000000)], np.int32)
+    a = ctx.fill(huge, blocks=True)["blocks"]
+    b = ctx.fill(huge, blocks=True, noise=True)
+    assert np.array_equal(a, b["blocks"])
+    assert np.array_equal(a == 0, b["noise"] < 0)
 
 
 def test_reference_interface_mirror(ctx, vox, oracle):

@@ -12,7 +12,9 @@ import voxb200  # noqa: E402
 
 ctx = voxb200.Context()
 coords = np.array([(x, 0, z) for z in range(-2, 2) for x in range(-2, 2)], np.int32)
-r = ctx.gen_mesh(coords, blocks=True)                                   # resolve, brick fill, count+scan, emit
+r = ctx.gen_mesh(coords, blocks=True)                                   # resolve, lattice fill, count+scan, emit
+f5 = ctx.fill(coords[:2], params=voxb200.default_noise_params(freq=0.9), blocks=True)         # hash (brick2) fill
+f6 = ctx.fill(np.array([(40000000, 0, -40000000)], np.int32), blocks=True)   # lattice kernel, boxes that do not fit
 m = np.full(len(coords), 15, np.uint8)
 r2 = ctx.gen_mesh(coords[:5], nbr_mask=m[:5])                           # halo fill
 f = ctx.fill(coords[:3], noise=True, census=True, occupancy=True)       # exact fill

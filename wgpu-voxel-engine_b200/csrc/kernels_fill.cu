@@ -144,120 +144,17 @@ vx_fill_kernel(const vx_fill_args a)
 //   t = s2*g;              |u + t| > B         -> sign(r) = sign(u + t)  skip 1 octave
 //   otherwise r = u + (t + s1), the reference's exact association.
 // The skip is taken only when it holds for the whole warp (no divergence); a
-// warp owns a 4 x 4 x 2 voxel brick per step, which keeps ~52 % / ~11 % of the
-// steps on the one-/two-octave shortcuts for the default terrain (rows of 32
-// voxels along x: 11 % / 0 %).  Blocks stay bit-exact by construction.
+// warp owns a 4 x 4 x 4 voxel cube per step, which stops ~11 % of the steps
+// after one octave and ~37 % after two on the default terrain (2.42 evaluations
+// per voxel; 2.03 if every voxel could decide alone).  Blocks stay bit-exact by
+// construction.  This kernel hashes every voxel corner (any frequency); the
+// lattice-table kernel below is the default-terrain path.
 //
 // CTA = 8 warps = (chunk, 4-wide z block); warp = 4-wide x block; lane =
-// (x & 3) | (z & 3) << 2 | (y & 1) << 4; 16 steps walk y.  Ballot nibbles are
+// (x & 3) | (z & 3) << 2 | (y & 1) << 4, two voxels (y, y + 2) per lane on the packed
+// FP32 instructions, so 8 steps of 4 x 4 x 4 voxels walk y.  Ballot nibbles are
 // gathered in shared memory into the 128 row words of the CTA's z block.
 // ---------------------------------------------------------------------------
-template <bool WANT_BLOCKS>
-__global__ void __launch_bounds__(256)
-vx_fill_brick_kernel(const vx_fill_args a)
-{
-    __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
-    // gradient coefficient table (2 KB, one column per lane & 7) placed on a 2048-byte boundary
-    // of the shared window inside a 4 KB buffer
-    __shared__ __align__(16) float4 s_lut_raw[2 * VXN_LUT_FLOAT4S];
-    const uint32_t lut_raw = (uint32_t)__cvta_generic_to_shared(s_lut_raw);
-    const uint32_t lut_base = (lut_raw + 2047u) & ~2047u;
-    float4 *s_lut = s_lut_raw + ((lut_base - lut_raw) >> 4);
-    if (threadIdx.x < VXN_LUT_FLOAT4S) s_lut[threadIdx.x] = vxn_grad_coeffs(threadIdx.x >> 3);
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
-    const vxn_lut_ref lut_lane = lut_base + (lane & 7u) * 16u;
-    const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
-    const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
-    const float ox = (float)(int32_t)((uint32_t)cx * 32u);
-    const float oy = (float)(int32_t)((uint32_t)cz * 32u);
-    const float oz = (float)(int32_t)((uint32_t)cy * 32u);
-    const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
-    const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
-    const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
-    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
-    const uint32_t seed = (uint32_t)a.p.seed;
-
-    float hx[3], hy[3], hxy[3];
-    hx[0] = __fmul_rn(sx, freq);
-    hy[0] = __fmul_rn(sy, freq);
-    hxy[0] = __fadd_rn(hx[0], hy[0]);
-#pragma unroll
-    for (int o = 1; o < 3; ++o) {
-        hx[o] = __fmul_rn(hx[o - 1], lac);
-        hy[o] = __fmul_rn(hy[o - 1], lac);
-        hxy[o] = __fadd_rn(hx[o], hy[o]);
-    }
-    const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
-    const float thr1 = a.thr1, thr2 = a.thr2;
-
-    const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
-    uint32_t my_word = 0;
-#pragma unroll 1
-    for (uint32_t it = 0; it < 16u; ++it) {
-        const uint32_t y = 2u * it + yy;
-        const float z0 = __fmul_rn(__fadd_rn(oz, (float)y), freq);
-        const float z1 = __fmul_rn(z0, lac);
-        const float z2 = __fmul_rn(z1, lac);
-        // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
-        bool solid, certain;
-        const float u = __fmul_rn(vxn_simplex3_sign<true>(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
-        if (__all_sync(VX_FULL, fabsf(u) > thr2 + errm)) {
-            solid = u < 0.0f;
-            certain = true;
-        } else {
-            const float ut = __fmaf_rn(vxn_simplex3_sign<true>(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1, u);
-            if (__all_sync(VX_FULL, fabsf(ut) > thr1 + errm)) {
-                solid = ut < 0.0f;
-                certain = true;
-            } else {
-                const float r = __fadd_rn(ut, vxn_simplex3_sign<true>(hx[0], hy[0], z0, hxy[0], seed, lut_lane));
-                solid = r < 0.0f;
-                certain = fabsf(r) > errm;
-            }
-        }
-        if (__any_sync(VX_FULL, !certain)) {
-            // some lane is within the margin of zero: redo the step with the reference's exact
-            // operation order (separately rounded, r = u + (t + s1))
-            const float ue = __fmul_rn(vxn_simplex3_sign<false>(hx[2], hy[2], z2, hxy[2], seed, lut_lane), amp2);
-            const float te = __fmul_rn(vxn_simplex3_sign<false>(hx[1], hy[1], z1, hxy[1], seed, lut_lane), amp1);
-            const float s1 = vxn_simplex3_sign<false>(hx[0], hy[0], z0, hxy[0], seed, lut_lane);
-            solid = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
-        }
-        const uint32_t word = __ballot_sync(VX_FULL, solid);     // bit = yy*16 + zz*4 + xx
-        if (lane == it) my_word = word;                          // lane `it` keeps the word of step `it`
-    }
-    if (lane < 16u) {
-        // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
-#pragma unroll
-        for (uint32_t p8 = 0; p8 < 8u; ++p8)
-            nib[2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
-    }
-    __syncthreads();
-
-    // 128 row words of this z block: row (y, zblk*4 + zz) = 8 nibbles, one per x block
-    const uint32_t t = threadIdx.x;
-    const uint32_t rr = t >> 1, half = t & 1u;                  // row 0..127, 16-voxel half
-    const uint32_t y = rr >> 2, zq = rr & 3u;
-    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[y][zq][0]);
-    // pack the low nibble of each of the 8 bytes into one 32-bit word
-    const uint32_t lo = (nb.x & 0x0f0f0f0fu), hi = (nb.y & 0x0f0f0f0fu);
-    const uint32_t plo = (lo | (lo >> 4)) & 0x00ff00ffu, phi = (hi | (hi >> 4)) & 0x00ff00ffu;
-    const uint32_t w16lo = (plo | (plo >> 8)) & 0xffffu, w16hi = (phi | (phi >> 8)) & 0xffffu;
-    const uint32_t wordv = w16lo | (w16hi << 16);
-    if (half == 0) a.occ[(size_t)item * VX_ROWS + y * 32u + zblk * 4u + zq] = wordv;
-    if (WANT_BLOCKS) {
-        const uint32_t air16 = ~(wordv >> (16u * half)) & 0xffffu;
-        uint4 v;
-        v.x = (((air16 >> 0) & 15u) * 0x00204081u & 0x01010101u) << 1;
-        v.y = (((air16 >> 4) & 15u) * 0x00204081u & 0x01010101u) << 1;
-        v.z = (((air16 >> 8) & 15u) * 0x00204081u & 0x01010101u) << 1;
-        v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
-        *reinterpret_cast<uint4 *>(a.blocks + (size_t)item * VX_VOXELS + (size_t)y * 1024u +
-                                   (zblk * 4u + zq) * 32u + half * 16u) = v;
-    }
-}
-
 template <bool WANT_BLOCKS>
 __global__ void __launch_bounds__(256, 2)
 vx_fill_brick2_kernel(const vx_fill_args a)

@@ -124,34 +124,35 @@ static int noise_chunk_lattice(const int32_t *c, int32_t seed, float freq, float
     static char tab[3][VXL_TAB_BYTES];
     int unfit = 0;
     for (int zblk = 0; zblk < 8; ++zblk) {
-        int32_t lo[3][3], hi[3][3];
+        float lo[3][3], hi[3][3];
         bool fit = true;
-        uint32_t org[3];
+        float4 og[3];
         for (int o = 0; o < 3; ++o) {
             for (int cn = 0; cn < 8; ++cn) {
                 float fx = (ox + ((cn & 1) ? 31.0f : 0.0f)) * freq;
                 float fy = (oy + (float)(zblk * 4 + ((cn & 2) ? 3 : 0))) * freq;
                 float fz = (oz + ((cn & 4) ? 31.0f : 0.0f)) * freq;
                 for (int q = 0; q < o; ++q) { fx *= lac; fy *= lac; fz *= lac; }
-                int32_t v[3];
-                vxl_cell_index(fx, fy, fz, fx + fy, &v[0], &v[1], &v[2]);
+                float v[3];
+                vxl_cell_floor(fx, fy, fz, fx + fy, &v[0], &v[1], &v[2]);
                 for (int d = 0; d < 3; ++d) {
                     if (cn == 0 || v[d] < lo[o][d]) lo[o][d] = v[d];
                     if (cn == 0 || v[d] > hi[o][d]) hi[o][d] = v[d];
                 }
             }
-            for (int d = 0; d < 3; ++d) fit = fit && (uint32_t)(hi[o][d] - lo[o][d]) <= VXL_DIM - 2u;
-            org[o] = 0u - ((uint32_t)lo[o][0] * VXL_SI + (uint32_t)lo[o][1] * VXL_SJ + (uint32_t)lo[o][2] * VXL_SK);
+            for (int d = 0; d < 3; ++d) fit = fit && vxl_axis_fits(lo[o][d], hi[o][d]);
+            og[o] = make_float4(lo[o][0], lo[o][1], lo[o][2], VXL_MAGIC);
         }
         if (!fit) { ++unfit; continue; }
         for (int o = 0; o < 3; ++o) {
             memset(tab[o], 0xff, VXL_TAB_BYTES);          // NaN pattern: reading an unbuilt entry poisons the result
-            for (int32_t i = lo[o][0]; i <= hi[o][0] + 1; ++i)
-                for (int32_t j = lo[o][1]; j <= hi[o][1] + 1; ++j)
-                    for (int32_t k = lo[o][2]; k <= hi[o][2] + 1; ++k) {
+            const int32_t i0 = (int32_t)lo[o][0], j0 = (int32_t)lo[o][1], k0 = (int32_t)lo[o][2];
+            for (int32_t i = i0; i <= (int32_t)hi[o][0] + 1; ++i)
+                for (int32_t j = j0; j <= (int32_t)hi[o][1] + 1; ++j)
+                    for (int32_t k = k0; k <= (int32_t)hi[o][2] + 1; ++k) {
                         const float4 e = vxl_entry((uint32_t)seed, i, j, k);
-                        memcpy(tab[o] + (uint32_t)(i - lo[o][0]) * VXL_SI + (uint32_t)(j - lo[o][1]) * VXL_SJ +
-                                   (uint32_t)(k - lo[o][2]) * VXL_SK, &e, 16);
+                        memcpy(tab[o] + (uint32_t)(i - i0) * VXL_SI + (uint32_t)(j - j0) * VXL_SJ +
+                                   (uint32_t)(k - k0) * VXL_SK, &e, 16);
                     }
         }
         for (int zz = zblk * 4; zz < zblk * 4 + 4; ++zz)
@@ -165,9 +166,9 @@ static int noise_chunk_lattice(const int32_t *c, int32_t seed, float freq, float
                         const int ya = 4 * it + yy, yb = ya + 2;
                         const float za0 = (oz + (float)ya) * freq, zb0 = (oz + (float)yb) * freq;
                         const float za1 = za0 * lac, zb1 = zb0 * lac, za2 = za1 * lac, zb2 = zb1 * lac;
-                        const float2 s3 = vxn_simplex3_lattice_x2(VX2(hx[2]), VX2(hy[2]), make_float2(za2, zb2), VX2(hxy[2]), org[2], tab[2]);
-                        const float2 s2 = vxn_simplex3_lattice_x2(VX2(hx[1]), VX2(hy[1]), make_float2(za1, zb1), VX2(hxy[1]), org[1], tab[1]);
-                        const float2 s1 = vxn_simplex3_lattice_x2(VX2(hx[0]), VX2(hy[0]), make_float2(za0, zb0), VX2(hxy[0]), org[0], tab[0]);
+                        const float2 s3 = vxn_simplex3_lattice_x2(VX2(hx[2]), VX2(hy[2]), make_float2(za2, zb2), VX2(hxy[2]), og[2], tab[2]);
+                        const float2 s2 = vxn_simplex3_lattice_x2(VX2(hx[1]), VX2(hy[1]), make_float2(za1, zb1), VX2(hxy[1]), og[1], tab[1]);
+                        const float2 s1 = vxn_simplex3_lattice_x2(VX2(hx[0]), VX2(hy[0]), make_float2(za0, zb0), VX2(hxy[0]), og[0], tab[0]);
                         const float2 r = __fadd2_rn(__ffma2_rn(s2, VX2(amp1), __fmul2_rn(s3, VX2(amp2))), s1);
                         out[lane + 32 * zz + 1024 * ya] = r.x;
                         out[lane + 32 * zz + 1024 * yb] = r.y;

@@ -311,7 +311,8 @@ vx_fill_lattice_kernel(const vx_fill_args a)
 {
     __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
     __shared__ __align__(16) unsigned char s_tab[3][VXL_TAB_BYTES];
-    __shared__ int32_t s_box[3][6];                       // per octave: min i, j, k, max i, j, k
+    __shared__ float s_box[3][6];                         // per octave: min i, j, k, max i, j, k (exact integers)
+    __shared__ float4 s_og[3];                            // per octave: box minimum and 2^23 + table address
     const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
     const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
     const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
@@ -321,7 +322,7 @@ vx_fill_lattice_kernel(const vx_fill_args a)
     const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
     const uint32_t seed = (uint32_t)a.p.seed;
 
-    // ---- index box of this CTA's 32 x 4 x 32 voxels, per octave: floor indices at the 8 corners
+    // ---- index box of this CTA's 32 x 4 x 32 voxels, per octave: floor values at the 8 corners
     if (threadIdx.x < 32u) {
         const uint32_t o = min(lane >> 3, 2u), c = lane & 7u;
         float fx = __fmul_rn(__fadd_rn(ox, (c & 1u) ? 31.0f : 0.0f), freq);
@@ -330,33 +331,30 @@ vx_fill_lattice_kernel(const vx_fill_args a)
 #pragma unroll
         for (uint32_t q = 0; q < 2u; ++q)
             if (q < o) { fx = __fmul_rn(fx, lac); fy = __fmul_rn(fy, lac); fz = __fmul_rn(fz, lac); }
-        int32_t lo[3], hi[3];
-        vxl_cell_index(fx, fy, fz, __fadd_rn(fx, fy), &lo[0], &lo[1], &lo[2]);
+        float lo[3], hi[3];
+        vxl_cell_floor(fx, fy, fz, __fadd_rn(fx, fy), &lo[0], &lo[1], &lo[2]);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             hi[d] = lo[d];
 #pragma unroll
             for (int m = 1; m < 8; m <<= 1) {
-                lo[d] = min(lo[d], __shfl_xor_sync(VX_FULL, lo[d], m));
-                hi[d] = max(hi[d], __shfl_xor_sync(VX_FULL, hi[d], m));
+                lo[d] = fminf(lo[d], __shfl_xor_sync(VX_FULL, lo[d], m));
+                hi[d] = fmaxf(hi[d], __shfl_xor_sync(VX_FULL, hi[d], m));
             }
         }
         if (c == 0u && lane < 24u) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) { s_box[o][d] = lo[d]; s_box[o][3 + d] = hi[d]; }
+            s_og[o] = make_float4(lo[0], lo[1], lo[2],
+                                  VXL_MAGIC + (float)(uint32_t)__cvta_generic_to_shared(&s_tab[o][0]));
         }
     }
     __syncthreads();
     bool fit = true;
-    uint32_t org[3];
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        const uint32_t ni = (uint32_t)(s_box[o][3] - s_box[o][0]), nj = (uint32_t)(s_box[o][4] - s_box[o][1]),
-                       nk = (uint32_t)(s_box[o][5] - s_box[o][2]);
-        fit = fit && ni <= VXL_DIM - 2u && nj <= VXL_DIM - 2u && nk <= VXL_DIM - 2u;
-        org[o] = (uint32_t)__cvta_generic_to_shared(&s_tab[o][0]) -
-                 ((uint32_t)s_box[o][0] * VXL_SI + (uint32_t)s_box[o][1] * VXL_SJ + (uint32_t)s_box[o][2] * VXL_SK);
-    }
+    for (int o = 0; o < 3; ++o)
+        fit = fit && vxl_axis_fits(s_box[o][0], s_box[o][3]) && vxl_axis_fits(s_box[o][1], s_box[o][4]) &&
+              vxl_axis_fits(s_box[o][2], s_box[o][5]);
     const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
     const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
     const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
@@ -367,9 +365,10 @@ vx_fill_lattice_kernel(const vx_fill_args a)
         // ---- hash every lattice point of the three boxes once (+1 per axis for the far corners)
 #pragma unroll 1
         for (int o = 0; o < 3; ++o) {
-            const int32_t i0 = s_box[o][0], j0 = s_box[o][1], k0 = s_box[o][2];
-            const uint32_t ni = (uint32_t)(s_box[o][3] - i0) + 2u, nj = (uint32_t)(s_box[o][4] - j0) + 2u,
-                           nk = (uint32_t)(s_box[o][5] - k0) + 2u;
+            const int32_t i0 = (int32_t)s_box[o][0], j0 = (int32_t)s_box[o][1], k0 = (int32_t)s_box[o][2];
+            const uint32_t ni = (uint32_t)(int32_t)(s_box[o][3] - s_box[o][0]) + 2u,
+                           nj = (uint32_t)(int32_t)(s_box[o][4] - s_box[o][1]) + 2u,
+                           nk = (uint32_t)(int32_t)(s_box[o][5] - s_box[o][2]) + 2u;
             for (uint32_t e = threadIdx.x; e < ni * 64u; e += 256u) {
                 const uint32_t ea = e >> 6, eb = (e >> 3) & 7u, ec = e & 7u;
                 if (eb < nj && ec < nk)
@@ -403,19 +402,19 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
             // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
             bool solid_a, solid_b, certain;
-            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], org[2], 0), VX2(amp2));
+            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], s_og[2], 0), VX2(amp2));
             if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
                 solid_a = u.x < 0.0f;
                 solid_b = u.y < 0.0f;
                 certain = true;
             } else {
-                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], org[1], 0), VX2(amp1), u);
+                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], s_og[1], 0), VX2(amp1), u);
                 if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
                     solid_a = ut.x < 0.0f;
                     solid_b = ut.y < 0.0f;
                     certain = true;
                 } else {
-                    const float2 r = __fadd2_rn(ut, vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], org[0], 0));
+                    const float2 r = __fadd2_rn(ut, vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], s_og[0], 0));
                     solid_a = r.x < 0.0f;
                     solid_b = r.y < 0.0f;
                     certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;

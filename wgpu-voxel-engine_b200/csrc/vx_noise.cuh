@@ -345,17 +345,26 @@ __device__ __forceinline__ float4 vxl_entry(uint32_t seed, int32_t i, int32_t j,
     return vxn_grad_coeffs(((h >> 13) ^ h) & 15u);
 }
 
-// floor indices of one voxel: the cell selection's own sequence (used for the box corners)
-__device__ __forceinline__ void vxl_cell_index(float x, float y, float z, float xy, int32_t *i, int32_t *j, int32_t *k)
+// floor values (exact integers in f32) of one voxel: the cell selection's own sequence (box corners)
+__device__ __forceinline__ void vxl_cell_floor(float x, float y, float z, float xy, float *i, float *j, float *k)
 {
     const float f = __fmul_rn(VXN_F3, __fadd_rn(xy, z));
-    *i = __float2int_rz(floorf(__fadd_rn(x, f)));
-    *j = __float2int_rz(floorf(__fadd_rn(y, f)));
-    *k = __float2int_rz(floorf(__fadd_rn(z, f)));
+    *i = floorf(__fadd_rn(x, f));
+    *j = floorf(__fadd_rn(y, f));
+    *k = floorf(__fadd_rn(z, f));
+}
+// a box is usable if it spans at most VXL_DIM - 2 cells per axis and its indices convert exactly
+__device__ __forceinline__ bool vxl_axis_fits(float lo, float hi)
+{
+    return __fsub_rn(hi, lo) <= (float)(VXL_DIM - 2u) && fabsf(lo) < 1073741824.0f && fabsf(hi) < 1073741824.0f;
 }
 
-// org = (table base) - (i0*SI + j0*SJ + k0*SK) mod 2^32, (i0, j0, k0) the box minimum.
-__device__ __forceinline__ float2 vxn_simplex3_lattice_x2(float2 x, float2 y, float2 z, float2 xy, uint32_t org,
+// Table addresses are formed in f32: (floor - box minimum) are exact small integers, the strides and
+// the table base are too, and adding 2^23 leaves  base + i*SI + j*SJ + k*SK  in the low mantissa bits:
+// 3 FADD2 + 3 FFMA2 + one LOP3 per element instead of 3 F2I (XU pipe) + 3 IMAD per element.
+//   og = (box min i, j, k as f32,  2^23 + table base)   [device: base = shared-window address; host: 0]
+#define VXL_MAGIC 8388608.0f
+__device__ __forceinline__ float2 vxn_simplex3_lattice_x2(float2 x, float2 y, float2 z, float2 xy, float4 og,
                                                           vxl_tab_ref tab)
 {
     // ---- cell selection: the reference's exact operation sequence per element ------------------
@@ -364,6 +373,9 @@ __device__ __forceinline__ float2 vxn_simplex3_lattice_x2(float2 x, float2 y, fl
     const float2 xf = make_float2(floorf(xs.x), floorf(xs.y));
     const float2 yf = make_float2(floorf(ys.x), floorf(ys.y));
     const float2 zf = make_float2(floorf(zs.x), floorf(zs.y));
+    const float2 lin = __ffma2_rn(__fadd2_rn(xf, VX2(-og.x)), VX2((float)VXL_SI),
+                                  __ffma2_rn(__fadd2_rn(yf, VX2(-og.y)), VX2((float)VXL_SJ),
+                                             __ffma2_rn(__fadd2_rn(zf, VX2(-og.z)), VX2((float)VXL_SK), VX2(og.w))));
 
     const float2 g = vx2_scale_unfused(VXN_G3, __fadd2_rn(__fadd2_rn(xf, yf), zf));
     const float2 x0 = __fadd2_rn(x, vx2_neg(__fadd2_rn(xf, vx2_neg(g))));
@@ -378,10 +390,7 @@ __device__ __forceinline__ float2 vxn_simplex3_lattice_x2(float2 x, float2 y, fl
     for (int e = 0; e < 2; ++e) {
         const float ex0 = e ? x0.y : x0.x, ey0 = e ? y0.y : y0.x, ez0 = e ? z0.y : z0.x;
         const float exm = e ? xm.y : xm.x, eym = e ? ym.y : ym.x, ezm = e ? zm.y : zm.x;
-        const uint32_t xi = (uint32_t)__float2int_rz(e ? xf.y : xf.x);
-        const uint32_t yj = (uint32_t)__float2int_rz(e ? yf.y : yf.x);
-        const uint32_t zk = (uint32_t)__float2int_rz(e ? zf.y : zf.x);
-        const uint32_t base = xi * VXL_SI + (yj * VXL_SJ + (zk * VXL_SK + org));
+        const uint32_t base = __float_as_uint(e ? lin.y : lin.x) & 0x7fffffu;
         const bool xy_ = ex0 >= ey0, yz_ = ey0 >= ez0, xz_ = ex0 >= ez0;
         const bool i1 = xy_ && xz_, j1 = !xy_ && yz_, k1 = !xz_ && !yz_;
         const bool i2 = xy_ || xz_, j2 = !xy_ || yz_, k2 = !(xz_ && yz_);

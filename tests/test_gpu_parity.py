@@ -554,3 +554,36 @@ def test_concurrent_callers_like_the_uvth_pool(ctx, vox):
     assert len(results) == 8 * 3 * len(jobs)
     for (tid, rep, k, kind), b in results.items():
         assert b == (serial[k] if kind == "m" else serial_vis[k]), (tid, rep, k, kind)
+
+
+def test_two_batches_in_flight_on_two_contexts(ctx, vox):
+    """bench.py and INTEGRATION.md 3 keep two batches in flight: device-resident calls alternate between two
+    contexts, each on its own stream with its own outputs, and nothing synchronises in between.  Every batch
+    must equal the result of the same batch run alone."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n, cap = 256, 256 * 8192
+    batches = [_grid(16 * (i % 3) - 16, 16 * (i // 3) - 8, 16, 16) for i in range(6)]
+    alone = [ctx.gen_mesh(b) for b in batches]
+    ctxs = [vox.Context(devices=[0]) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    d_coords = [torch.from_numpy(b).to(dev) for b in batches]
+    outs = [dict(c=torch.zeros(n, dtype=torch.int32, device=dev), o=torch.zeros(n + 1, dtype=torch.int64, device=dev),
+                 i=torch.empty(cap * 17, dtype=torch.int32, device=dev), s=torch.zeros(4, dtype=torch.int32, device=dev))
+            for _ in batches]                                            # one output set per batch: read after the flush
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for k in range(len(batches)):
+            j, o = k % 2, outs[k]
+            ctxs[j].gen_mesh_device(d_coords[k].data_ptr(), n, o["c"].data_ptr(), o["o"].data_ptr(), o["i"].data_ptr(), cap,
+                                    status_ptr=o["s"].data_ptr(), stream=streams[j].cuda_stream)
+    torch.cuda.synchronize()
+    for k, o in enumerate(outs):
+        assert int(o["s"][0].item()) == 0
+        assert np.array_equal(o["c"].cpu().numpy().astype(np.uint32), alone[k].counts)
+        total = int(o["o"][n].item())
+        assert total == alone[k].total
+        got = o["i"][:total * 17].cpu().numpy().view(np.uint8)
+        assert got.tobytes() == alone[k].instances.tobytes()
+    for c in ctxs:
+        c.close()

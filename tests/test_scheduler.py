@@ -115,3 +115,77 @@ def test_batched_scheduler_reaches_the_reference_state(vox, oracle):
         adj = [world2.chunks[n].cubes if n in world2.chunks else None for n in neighbours(pos)]
         assert _canon(world2.meshes[pos].instance_buffer).tobytes() == _canon(oracle.create_mesh(pos, ch.cubes, adj)).tobytes()
     ctx.close()
+
+
+def _build_cpp_sched_demo(vox, tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "wgpu-voxel-engine_b200", "host")
+    exe = str(tmp_path / "host_sched_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(host, "host_sched_demo.cpp"),
+                           "-L" + os.path.dirname(vox.SO_PATH), "-lvoxb200",
+                           "-Wl,-rpath," + os.path.dirname(vox.SO_PATH), "-o", exe])
+    return exe
+
+
+def test_cpp_scheduler_replay_equals_the_python_specification(vox, tmp_path):
+    """CPU only.  host/chunk_builder.hpp (C++ mirror of the batched scheduler) replays the reference's queues
+    to the same per-chunk neighbour snapshots, in the same order, as chunk_builder.py -- over random loaded
+    sets, ring subsets and both 'entered a new chunk' cases."""
+    import subprocess
+    from importlib import import_module
+    cb = import_module(vox.__name__ + ".chunk_builder") if hasattr(vox, "__name__") else None
+    exe = _build_cpp_sched_demo(vox, tmp_path)
+    rng = np.random.default_rng(11)
+    for case in range(12):
+        pc = tuple(int(v) for v in (rng.integers(-6, 7), 0, rng.integers(-6, 7)))
+        entered = bool(case % 2)
+        around = [(pc[0] + dx, 0, pc[2] + dz) for dx in range(-5, 6) for dz in range(-5, 6)]
+        loaded = {c for c in around if rng.random() < (0.0 if case < 2 else 0.35)}
+        ring = [c for c in cb.ring_coords(pc) if c not in loaded and rng.random() < 0.6]
+        gen = vox.ChunkGenerator(device=None)
+        player = vox.Player((pc[0] * 32 + 5.0, 16.0, pc[2] * 32 + 5.0))
+        snap, _ = gen._replay(entered, player, set(loaded), ring)
+        text = "%d %d %d %d\n%d\n" % (entered, pc[0], pc[1], pc[2], len(loaded))
+        text += "".join("%d %d %d\n" % c for c in sorted(loaded)) + "%d\n" % len(ring) + "".join("%d %d %d\n" % c for c in ring)
+        out = subprocess.check_output([exe, "replay"], input=text, text=True).splitlines()
+        assert out[0] == "ticks %d" % gen.replayed_ticks
+        got = [tuple(int(v) for v in line.split()[1:]) for line in out[1:]]
+        assert got == [c + (m,) for c, m in snap.items()], case
+
+
+@pytest.mark.gpu
+def test_cpp_scheduler_reaches_the_python_world(vox, tmp_path):
+    """The C++ ChunkGenerator driven through the same poses ends every pose with the world of the Python one
+    (chunks, cube ids, InstanceRaw streams, draw gate), in one GPU batch per pose."""
+    import subprocess
+    exe = _build_cpp_sched_demo(vox, tmp_path)
+
+    def fnv(b, h):
+        for v in np.frombuffer(b, np.uint8).tolist():
+            h = ((h ^ v) * 16777619) & 0xFFFFFFFF
+        return h
+    for mode in ("reference", "converged"):
+        ctx = vox.Context()
+        gen, world, player = vox.ChunkGenerator(ctx, mode=mode), vox.World(), vox.Player(POSES[0][0])
+        text, want = "", []
+        for eye, yaw in POSES:
+            planes = _planes(eye, yaw)
+            text += " ".join("%.9g" % v for v in list(eye) + planes.reshape(-1).tolist()) + "\n"
+            player.update_pos(eye)
+            fr = vox.Frustum(planes, ctx)
+            gen.build_chunks(player, world, fr)
+            batch, ticks = gen.last_batch, gen.replayed_ticks
+            h, quads = 2166136261, 0
+            for pos in sorted(world.chunks):
+                h = fnv(np.array(pos, np.int32).tobytes(), h)
+                h = fnv(world.chunks[pos].cubes.tobytes(), h)
+                inst = _canon(world.meshes[pos].instance_buffer)
+                quads += len(inst)
+                h = fnv(inst.tobytes(), h)
+            drawn = len(world.visible_meshes(fr, ctx))
+            want.append("pose %d chunks %d meshes %d batch %d second_batch 0 ticks %d quads %d drawn %d digest %08x" % (
+                len(want), len(world.chunks), len(world.meshes), batch, ticks, quads, drawn, h))
+        ctx.close()
+        out = subprocess.check_output([exe, "run", mode], input=text, text=True).splitlines()
+        assert out == want, (mode, out, want)

@@ -9,8 +9,10 @@
 //   ChunkMesh { instance_buffer, instances_len }    chunk.rs:248-266 (bytes for create_buffer_init)
 //   Frustum::new / update / contains                frustum_culling.rs:10-45
 //   ChunkGenerator worker closure, batched          chunk_builder.rs:80-84
+//   (the batched scheduler itself -- World, Player, ChunkGenerator -- is chunk_builder.hpp)
 // Failures throw vox::Error (the reference panics: chunk_builder.rs:83,107,128).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -163,6 +165,13 @@ class Frustum {
     {
         Frustum f;
         f.update(global_matrix);
+        return f;
+    }
+    // from six planes (near, far, left, right, top, bottom; a, b, c, d each) computed elsewhere
+    static Frustum from_planes(const float planes[24])
+    {
+        Frustum f;
+        std::copy(planes, planes + 24, f.planes_.begin());
         return f;
     }
     void update(const float global_matrix[16]) { check(vx_planes_from_matrix(global_matrix, planes_.data())); }

@@ -587,3 +587,24 @@ def test_two_batches_in_flight_on_two_contexts(ctx, vox):
         assert got.tobytes() == alone[k].instances.tobytes()
     for c in ctxs:
         c.close()
+
+
+def test_fast_fill_paths_agree_with_the_exact_kernel_on_random_parameters(ctx, vox):
+    """Both fast kernels (lattice tables for |freq * lac^k| <= 0.1, per-voxel hashing above) and the lattice
+    kernel's per-CTA exact path, against the exact kernel, over random seeds / frequencies / lacunarities /
+    gains (either sign) and coordinates from the origin out to where f32 loses the cell."""
+    rng = np.random.default_rng(2024)
+    scales = [8, 300, 20000, 1500000, 50000000]
+    for case in range(24):
+        freq = float(np.exp(rng.uniform(np.log(0.004), np.log(0.4)))) * (1 if rng.random() < 0.8 else -1)
+        lac = float(rng.uniform(0.25, 2.2)) * (1 if rng.random() < 0.8 else -1)
+        gain = float(rng.uniform(0.4, 4.0)) * (1 if rng.random() < 0.8 else -1)
+        p = vox.default_noise_params(seed=int(rng.integers(0, 2 ** 31 - 1)), freq=freq, lacunarity=lac, gain=gain)
+        s = scales[case % len(scales)]
+        coords = np.stack([rng.integers(-s, s + 1, 6), rng.integers(-3, 4, 6), rng.integers(-s, s + 1, 6)], 1).astype(np.int32)
+        fast = ctx.fill(coords, params=p, blocks=True, occupancy=True)
+        slow = ctx.fill(coords, params=p, blocks=True, noise=True)
+        assert np.array_equal(fast["blocks"], slow["blocks"]), (case, freq, lac, gain, s)
+        assert np.array_equal(fast["blocks"] == 0, slow["noise"] < 0)
+        bits = np.unpackbits(fast["occupancy"].view(np.uint8), axis=1, bitorder="little")
+        assert np.array_equal(bits.astype(bool), fast["blocks"] != 2)

@@ -2,7 +2,14 @@
 // bitmasks (+ optional block ids / noise field).  Replaces
 // perlin_noise.rs:5-22 + chunk.rs:27-46 for thousands of chunks per launch.
 //
-// Work unit = one warp = one 32x32 voxel slab of one chunk:
+// Three kernels (dispatch in vx_launch_fill at the end of the file):
+//   vx_fill_lattice_kernel  default terrain: sign-only octave skipping, two voxels per thread on
+//                           packed FP32, corner gradients from per-CTA lattice tables
+//   vx_fill_brick2_kernel   the same with per-voxel hashing, for frequencies whose index box
+//                           cannot fit a table
+//   vx_fill_kernel          exact f32 noise field: noise / census outputs, halo slabs, octaves != 3
+//
+// vx_fill_kernel: work unit = one warp = one 32x32 voxel slab of one chunk:
 //   full-chunk mode: unit (chunk, z); lane = x; the warp walks y = 0..31.
 //     One __ballot_sync per y gives the occupancy word of row (y, z).
 //   halo mode: unit = one border slab of a chunk that is NOT in the batch

@@ -21,6 +21,10 @@ def main():
     ap.add_argument("--region", type=int, default=1024)
     ap.add_argument("--seeds", default="1")
     ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--freq", type=float, default=None)
+    ap.add_argument("--lacunarity", type=float, default=None)
+    ap.add_argument("--gain", type=float, default=None)
+    ap.add_argument("--origin", default="0,0,0", help="chunk coordinate of the region centre (x,y,z)")
     args = ap.parse_args()
     import torch
     import voxb200
@@ -37,13 +41,15 @@ def main():
     occ_exact = torch.zeros(nb * 1024, dtype=torch.int32, device=dev)
     nz = torch.zeros(1, dtype=torch.int64, device=dev)
     for seed in [int(v) for v in args.seeds.split(",")]:
-        p = voxb200.default_noise_params(seed=seed)
+        kw = {k: v for k, v in (("freq", args.freq), ("lacunarity", args.lacunarity), ("gain", args.gain)) if v is not None}
+        p = voxb200.default_noise_params(seed=seed, **kw)
+        ox, oy, oz = (int(v) for v in args.origin.split(","))
         voxels = mismatched_words = near = solid = 0
         t0 = time.time()
         for z0 in range(-R // 2, R // 2, rows):
             zs = np.arange(z0, min(z0 + rows, R // 2), dtype=np.int32)
             z, x = np.meshgrid(zs, xs, indexing="ij")
-            c = np.stack([x.reshape(-1), np.zeros(x.size, np.int32), z.reshape(-1)], 1).astype(np.int32)
+            c = np.stack([x.reshape(-1) + ox, np.full(x.size, oy, np.int32), z.reshape(-1) + oz], 1).astype(np.int32)
             n = len(c)
             d_c = torch.from_numpy(c).to(dev)
             ctx.fill_device(d_c.data_ptr(), n, params=p, occ_ptr=occ_fast.data_ptr(), stream=st)
@@ -55,7 +61,7 @@ def main():
             near += int(nz.item())
             voxels += n * 32768
         print(json.dumps({"check": "fast fill kernel vs exact kernel, occupancy of every voxel",
-                          "region": "%dx%d chunks" % (R, R), "seed": seed, "voxels": voxels,
+                          "region": "%dx%d chunks" % (R, R), "origin": [ox, oy, oz], "params": kw, "seed": seed, "voxels": voxels,
                           "mismatched_occupancy_words": mismatched_words,
                           "near_threshold_voxels_abs_noise_le_1e-6": near, "seconds": round(time.time() - t0, 2)}))
         assert mismatched_words == 0

@@ -230,6 +230,13 @@ def test_fill_sign_only_shortcuts_are_exact(ctx, vox):
         b = ctx.fill(far, params=p, blocks=True, noise=True)
         assert np.array_equal(a, b["blocks"]), (gain, lac, freq, seed)
         assert np.array_equal(a == 0, b["noise"] < 0)
+    # non-finite parameters go to the exact kernel (NaN noise is never < 0: all AIR where it reaches the sum)
+    for kw in (dict(lacunarity=float("nan")), dict(gain=float("inf")), dict(freq=float("nan")), dict(lacunarity=float("inf"))):
+        p = vox.default_noise_params(**kw)
+        a = ctx.fill(far[:4], params=p, blocks=True)["blocks"]
+        b = ctx.fill(far[:4], params=p, blocks=True, noise=True)
+        assert np.array_equal(a, b["blocks"]), kw
+        assert np.array_equal(a == 0, b["noise"] < 0)
     # coordinates where the f32 spacing of the noise coordinate reaches the simplex cell size: some CTAs of
     # the lattice-table kernel no longer fit their index box and take the in-kernel exact path
     huge = np.array([(40000000, 0, -40000000), (3000000, 1, 3000000), (20000000, -5, 123), (-1500000, 0, 900000),

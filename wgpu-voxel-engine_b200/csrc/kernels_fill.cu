@@ -516,7 +516,8 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
     // (the coefficient-table gradient multiplies by 0, so coordinates must stay finite:
     //  |world * freq * lac^k| <= 2^31 * |freq| * max(1, lac^2) must not overflow f32)
     const float reach = 2147483648.0f * fabsf(a.p.freq) * fmaxf(1.0f, a.p.lacunarity * a.p.lacunarity);
-    const bool tame = isfinite(reach) && reach < 1e30f && isfinite(a.p.gain);
+    const bool tame = isfinite(reach) && reach < 1e30f && isfinite(a.p.gain) && isfinite(a.p.freq) &&
+                      isfinite(a.p.lacunarity);      // NaN / inf parameters: the exact kernel reproduces them as is
     if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && tame) {
         vx_fill_args b = a;
         // |simplex_3d| <= 0.030585; 0.0306 plus a relative slack far above the f32 rounding of u, t, u+t

@@ -116,3 +116,29 @@ def test_lattice_table_variant_is_bit_equal_to_the_scalar_fused_one(shim, coord,
     assert got.reshape(-1).sum() == (8 - unfit) * 4096
     assert np.array_equal(a.view(np.uint32)[got], b.view(np.uint32)[got])
     assert len(set(zb[~got])) == unfit
+
+
+def test_lattice_index_box_holds_for_random_chunks(shim):
+    """The 8-corner index box must contain the floor indices of every voxel of the z block (monotone rounding
+    argument, vx_noise.cuh): random chunks from the origin out to |chunk| = 6e7 and random parameters of either
+    sign.  An index outside its box would read a NaN-poisoned table entry (or miss the x1 values)."""
+    rng = np.random.default_rng(77)
+    fitted = unfitted = 0
+    for case in range(60):
+        scale = [40, 5000, 400000, 3000000, 60000000][case % 5]
+        coord = tuple(int(v) for v in (rng.integers(-scale, scale + 1), rng.integers(-4, 5), rng.integers(-scale, scale + 1)))
+        freq = float(np.exp(rng.uniform(np.log(0.003), np.log(0.12)))) * (1 if rng.random() < 0.75 else -1)
+        lac = float(rng.uniform(0.2, 1.6)) * (1 if rng.random() < 0.75 else -1)
+        gain = float(rng.uniform(0.3, 4.0))
+        seed = int(rng.integers(0, 2 ** 31 - 1))
+        c = np.array(coord, np.int32)
+        a = np.full(32768, np.nan, np.float32)
+        b = np.empty(32768, np.float32)
+        unfit = shim.shim_noise_chunk_lattice(c.ctypes.data, seed, freq, gain, lac, a.ctypes.data)
+        shim.shim_noise_chunk_x1(c.ctypes.data, seed, freq, gain, lac, 1, b.ctypes.data)
+        got = ~np.isnan(a)
+        assert got.sum() == (8 - unfit) * 4096, (case, coord, freq, lac)
+        assert np.array_equal(a.view(np.uint32)[got], b.view(np.uint32)[got]), (case, coord, freq, lac)
+        fitted += 8 - unfit
+        unfitted += unfit
+    assert fitted > 100 and unfitted > 20          # both outcomes are exercised

@@ -1,0 +1,28 @@
+"""Where do the ~150 us of a one-chunk vx_gen_mesh (config 1) go?"""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import voxb200
+ctx = voxb200.Context(devices=[0])
+for n in (1, 9, 81):
+    side = int(np.sqrt(n))
+    c = np.array([(x, 0, z) for z in range(side) for x in range(side)], np.int32)
+    m = np.full(n, 15 if n == 1 else 0, np.uint8)
+    kw = dict(nbr_mask=m) if n == 1 else {}
+    for _ in range(20):
+        ctx.gen_mesh(c, **kw)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        r = ctx.gen_mesh(c, **kw)
+    dt = (time.perf_counter() - t0) / 200
+    ctx.set_timing(True)
+    for _ in range(50):
+        ctx.gen_mesh(c, **kw)
+    kt = ctx.get_timing()
+    ctx.set_timing(False)
+    print("n=%d quads=%d host latency %.1f us; kernels (us): %s" % (
+        n, r.total, dt * 1e6, {k: round(1e3 * ms / ln, 1) for k, (ms, ln) in kt.items() if ln}))
+    t0 = time.perf_counter()
+    for _ in range(200):
+        ctx.fill(c, blocks=True)
+    print("      vx_fill (blocks to host) %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))

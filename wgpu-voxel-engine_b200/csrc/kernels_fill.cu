@@ -29,9 +29,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 vx_fill_kernel(const vx_fill_args a)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t unit = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    uint32_t unit = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     uint32_t limit = a.max_units;
-    if (HALO) limit = min(limit, *a.halo_count);
+    // halo slabs are few and sit on the latency path of short lists: four warps share one slab (8 rows each)
+    const uint32_t yq = HALO ? (unit & 3u) : 0u;
+    if (HALO) {
+        unit >>= 2;
+        limit = min(limit, *a.halo_count);
+    }
     if (unit >= limit) return;
 
     int32_t cx, cy, cz;
@@ -81,8 +86,9 @@ vx_fill_kernel(const vx_fill_args a)
     float *noise_row = nullptr;
     if (WANT_NOISE) noise_row = a.noise + (size_t)item * VX_VOXELS + fixed_val * 32u + lane;
 
+    const uint32_t y_first = HALO ? yq * 8u : 0u, y_last = HALO ? y_first + 8u : 32u;
 #pragma unroll 2
-    for (uint32_t y = 0; y < 32u; ++y) {
+    for (uint32_t y = y_first; y < y_last; ++y) {
         float z = __fmul_rn(__fadd_rn(oz, (float)y), freq);
         float r = vxn_simplex3(hx[0], hy[0], z, hxy[0], seed);
         if (OCT > 0) {
@@ -109,7 +115,7 @@ vx_fill_kernel(const vx_fill_args a)
     }
 
     if (HALO) {
-        a.occ[(size_t)item * 32u + lane] = my_word;          // word y: bit = lane axis
+        if ((lane >> 3) == yq) a.occ[(size_t)item * 32u + lane] = my_word;   // word y: bit = lane axis
         return;
     }
     a.occ[(size_t)item * VX_ROWS + lane * 32u + fixed_val] = my_word;   // row (y = lane, z)
@@ -479,7 +485,8 @@ vx_fill_lattice_kernel(const vx_fill_args a)
 template <int OCT, bool HALO>
 cudaError_t launch_oct(const vx_fill_args &a, cudaStream_t s)
 {
-    const uint32_t grid = (a.max_units + kWarpsPerCta - 1) / kWarpsPerCta;
+    const uint32_t warps = HALO ? a.max_units * 4u : a.max_units;
+    const uint32_t grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid == 0) return cudaSuccess;
     const dim3 block(kWarpsPerCta * 32);
     if (HALO) {

@@ -406,10 +406,11 @@ __constant__ uint32_t c_tex[2][6] = {
 
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
-#ifndef VX_EMIT_SPLIT
-#define VX_EMIT_SPLIT 1
-#endif
-constexpr int kEmitSplit = VX_EMIT_SPLIT;   // CTAs per chunk
+// CTAs per chunk: 1 for batches that fill the GPU (2 and 4 were measured slower there: every CTA repeats
+// the chunk set-up), kEmitSplitSmall for short lists, where one CTA per chunk would leave most SMs idle
+// and the call is latency-bound (the reference's one-chunk-per-call site, chunk_builder.rs:80-84)
+constexpr int kEmitSplitSmall = 4;
+constexpr uint32_t kEmitSmallList = 148;     // lists up to this many chunks use kEmitSplitSmall
 constexpr int kLutStride = 20;               // words per LUT row (80 B: 16-B aligned, bank-spread)
 constexpr int kTileWords = 32 * 17 + 4;      // one warp tile (32 instances) + alignment lead
 #ifndef VX_STAGE_BUFS
@@ -452,7 +453,7 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 // PACKED = true writes one 32-bit quad record instead of the 68-byte instance (extension for
 // renderers that expand in the vertex shader): bits 0-4 x, 5-9 z, 10-14 y (= voxel idx),
 // 15-17 face (VX_LEFT..VX_UP), 18 block type (0 GRASS, 1 DIRT); the chunk is implied by offsets[].
-template <bool PACKED>
+template <bool PACKED, int kEmitSplit>
 __global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
 {
@@ -686,10 +687,17 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
 {
     if (len == 0) return cudaSuccess;
     static_assert(sizeof(EmitSmem) <= 64 * 1024, "emit kernel shared memory budget");
-    if (a.packed)
-        vx_mesh_emit_kernel<true><<<len * kEmitSplit, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
-    else
-        vx_mesh_emit_kernel<false><<<len * kEmitSplit, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+    if (len <= kEmitSmallList) {
+        if (a.packed)
+            vx_mesh_emit_kernel<true, kEmitSplitSmall><<<len * kEmitSplitSmall, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
+        else
+            vx_mesh_emit_kernel<false, kEmitSplitSmall><<<len * kEmitSplitSmall, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+    } else {
+        if (a.packed)
+            vx_mesh_emit_kernel<true, 1><<<len, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
+        else
+            vx_mesh_emit_kernel<false, 1><<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+    }
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -698,8 +706,11 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
 // the device current.
 cudaError_t vx_init_mesh_kernels()
 {
-    cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(EmitSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, kEmitSplitSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(EmitSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));

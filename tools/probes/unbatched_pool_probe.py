@@ -1,0 +1,30 @@
+"""The reference's un-batched call shape: T pool threads (uvth, main.rs:34-36), each building ONE chunk per call
+(Chunk::new + create_mesh, chunk_builder.rs:80-84).  Aggregate chunks/s with one shared context vs one context
+per thread."""
+import os, sys, time, threading
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import voxb200
+
+def run(T, own, reps=150):
+    shared = voxb200.Context(devices=[0])
+    ctxs = [voxb200.Context(devices=[0]) if own else shared for _ in range(T)]
+    m = np.array([15], np.uint8)
+    outs = [voxb200.PinnedBuffer(98304 * 68).view(np.uint8) for _ in range(T)]
+    def worker(t):
+        for r in range(reps):
+            c = np.array([[t * 7 + r % 5, 0, r]], np.int32)
+            ctxs[t].gen_mesh(c, nbr_mask=m, out=outs[t])
+    for t in range(T):
+        worker_t = threading.Thread(target=worker, args=(t,))
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    for c in ctxs[:1]:
+        c.gen_mesh(np.array([[0, 0, 0]], np.int32), nbr_mask=m)
+    t0 = time.perf_counter()
+    for th in ths: th.start()
+    for th in ths: th.join()
+    dt = time.perf_counter() - t0
+    return T * reps / dt
+
+for T in (1, 4, 16):
+    print("threads %2d: shared context %8.0f chunks/s   context per thread %8.0f chunks/s" % (T, run(T, False), run(T, True)))

@@ -63,7 +63,9 @@ class PinnedBuffer:
         p = C.c_void_p()
         check(_lib.lib().vx_host_alloc(C.byref(p), nbytes))
         self.ptr, self.nbytes = p.value, nbytes
-        self.array = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(self.ptr))[:nbytes]
+        raw = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
+        raw._vx_owner = self          # numpy views reach `raw` through .base: they keep the allocation alive
+        self.array = np.ctypeslib.as_array(raw)[:nbytes]
 
     def view(self, dtype, count=None):
         a = self.array.view(dtype)

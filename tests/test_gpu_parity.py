@@ -615,3 +615,35 @@ def test_fast_fill_paths_agree_with_the_exact_kernel_on_random_parameters(ctx, v
         assert np.array_equal(fast["blocks"] == 0, slow["noise"] < 0)
         bits = np.unpackbits(fast["occupancy"].view(np.uint8), axis=1, bitorder="little")
         assert np.array_equal(bits.astype(bool), fast["blocks"] != 2)
+
+
+def test_short_list_path_pinned_and_pageable_outputs(ctx, vox, oracle):
+    """Lists of up to 32 chunks take the one-synchronisation path of vx_gen_mesh: into a pinned caller buffer
+    the emit kernel writes directly over PCIe, into pageable memory through the arena -- same bytes either
+    way, equal to the oracle, for 1..32 chunks, with and without block output, also in packed form."""
+    pinned = vox.PinnedBuffer(32 * 98304 * 68)
+    for n in (1, 2, 7, 32):
+        coords = _grid(-3, 5, n, 1) if n < 32 else _grid(-4, -4, 8, 4)
+        masks = np.random.default_rng(n).integers(0, 16, size=n).astype(np.uint8)
+        cubes = [oracle.generate_terrain(c) for c in coords]
+        want = [oracle.create_mesh(c, cubes[i], [oracle.generate_terrain(nc) if (masks[i] >> k) & 1 else None
+                                                 for k, nc in enumerate(_neighbours(c))]) for i, c in enumerate(coords)]
+        want_all = np.concatenate(want)
+        a = ctx.gen_mesh(coords, nbr_mask=masks, blocks=True)                          # pageable numpy output
+        b = ctx.gen_mesh(coords, nbr_mask=masks, out=pinned.view(np.uint8))            # pinned: zero-copy emit
+        for r in (a, b):
+            assert r.counts.tolist() == [len(w) for w in want]
+            assert r.offsets.tolist() == np.concatenate([[0], np.cumsum([len(w) for w in want])]).tolist()
+            assert _canon(r.instances).tobytes() == _canon(want_all).tobytes()
+        assert np.array_equal(a.blocks, np.stack(cubes))
+        pk = ctx.gen_mesh_packed(coords, nbr_mask=masks)
+        pk2 = ctx.gen_mesh_packed(coords, nbr_mask=masks, out=pinned.view(np.uint32))
+        assert pk.total == a.total and np.array_equal(pk.instances, pk2.instances)
+    # capacity too small: error, counts still valid, nothing written past the buffer
+    small = vox.PinnedBuffer(100 * 68)
+    guard = small.view(np.uint8)
+    guard[:] = 0xAB
+    with pytest.raises(vox.VoxError) as e:
+        ctx.gen_mesh(_grid(0, 0, 2, 1), out=guard)
+    assert e.value.code == vox._lib.VX_ERR_CAPACITY
+    assert (guard == 0xAB).all()

@@ -16,7 +16,10 @@ r = ctx.gen_mesh(coords, blocks=True)                                   # resolv
 f5 = ctx.fill(coords[:2], params=voxb200.default_noise_params(freq=0.9), blocks=True)         # hash (brick2) fill
 f6 = ctx.fill(np.array([(40000000, 0, -40000000)], np.int32), blocks=True)   # lattice kernel, boxes that do not fit
 m = np.full(len(coords), 15, np.uint8)
-r2 = ctx.gen_mesh(coords[:5], nbr_mask=m[:5])                           # halo fill
+r2 = ctx.gen_mesh(coords[:5], nbr_mask=m[:5])                           # halo fill; short-list path, pageable output
+pin = voxb200.PinnedBuffer(5 * 98304 * 68)
+r3 = ctx.gen_mesh(coords[:5], nbr_mask=m[:5], out=pin.view(np.uint8))   # short-list path, emit straight into pinned host memory
+assert r3.total == r2.total and r3.instances.tobytes() == r2.instances.tobytes()
 f = ctx.fill(coords[:3], noise=True, census=True, occupancy=True)       # exact fill
 f4 = ctx.fill(coords[:2], params=voxb200.default_noise_params(octaves=4))   # generic octave loop
 g = np.indices((32, 32, 32)).sum(axis=0) & 1

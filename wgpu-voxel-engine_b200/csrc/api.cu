@@ -76,6 +76,8 @@ struct DevBuf {
 
 constexpr size_t kArenaBytes = size_t(256) << 20;                      // per instance arena
 constexpr size_t kSliceBytes = size_t(256) << 20;                      // staging for fill / frustum outputs
+constexpr size_t kShortList = 32;                                      // lists up to this long take the one-sync path
+constexpr size_t kStageBytes = 4096;                                   // >= kShortList * (12 + 1 + 4 + 8) + 8 + 16
 
 struct Dev {
     int id = 0;
@@ -86,6 +88,7 @@ struct Dev {
     DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_in, counts, offsets, small, blocks, noise,
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
+    unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
     uint64_t launches = 0;
     // optional per-kernel-class CUDA-event timing (vx_set_timing)
     bool timing = false;
@@ -369,6 +372,7 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
         if (e == cudaSuccess) e = d.small.ensure(64);
         if (e == cudaSuccess) e = cudaMemset(d.small.p, 0, 64);
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_small, 64, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_stage, kStageBytes, cudaHostAllocPortable);
         if (e != cudaSuccess) {
             int r = cuda_fail(e, "context setup", __LINE__);
             vx_destroy(ctx);
@@ -390,6 +394,7 @@ void vx_destroy(vx_ctx *ctx)
                           &d.vis, &d.bits, &d.mesh_mask})
             b->release();
         if (d.h_small) cudaFreeHost(d.h_small);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
         for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
         for (auto &ev : d.free_events) {
             cudaEventDestroy(ev.first);
@@ -693,6 +698,93 @@ int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, cons
                                 stream, true);
 }
 
+// ---------------------------------------------------------------------------
+// Short lists (the reference's one-chunk-per-call site, chunk_builder.rs:80-84): the call is latency-
+// bound, so everything is issued before the host waits ONCE.  Coordinates and masks go up in one copy
+// from pinned staging; the emit is launched speculatively behind the count (its capacity check runs on
+// the device); counts, offsets and the status word come back in one pinned copy.  If the caller's
+// instance buffer is pinned host memory (vx_host_alloc) the emit kernel writes straight into it over
+// PCIe and no second copy or synchronisation exists at all; otherwise the instances go through the
+// arena and one more copy of exactly `total` records.
+// ---------------------------------------------------------------------------
+static int gen_mesh_short(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params &p,
+                          const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, unsigned char *instances,
+                          size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
+{
+    Dev &d = ctx->devs[0];
+    const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
+    const uint32_t nn = (uint32_t)n;
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = d.stream;
+    // upload: [coords 12 n][mask n]
+    const size_t up = 12 * n + (nbr_mask ? n : 0);
+    CK(d.coords.ensure(up));
+    std::memcpy(d.h_stage, coords, 12 * n);
+    if (nbr_mask) std::memcpy(d.h_stage + 12 * n, nbr_mask, n);
+    CK(cudaMemcpyAsync(d.coords.p, d.h_stage, up, cudaMemcpyHostToDevice, s));
+    const uint8_t *d_mask = nbr_mask ? d.coords.as<uint8_t>() + 12 * n : nullptr;
+    // download block on the device: [offsets 8 (n + 1)][counts 4 n], contiguous so ONE copy brings both back
+    const size_t off_bytes = 8 * (n + 1), down = off_bytes + 4 * n;
+    CK(d.offsets.ensure(down));
+    uint64_t *d_off = d.offsets.as<uint64_t>();
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d.offsets.as<unsigned char>() + off_bytes);
+    uint8_t *d_blocks = nullptr;
+    if (blocks_out) {
+        CK(d.blocks.ensure(n * VX_VOXELS));
+        d_blocks = d.blocks.as<uint8_t>();
+    }
+    CK(cudaMemsetAsync(d.st(), 0, 4, s));
+    RET(dev_gen_count(d, s, d.coords.as<int32_t>(), nn, 0, nn, p, d_mask, d_cnt, d_off, d_blocks));
+    // where the instances go: straight into a pinned caller buffer, else the arena
+    void *dev_out = nullptr;
+    size_t dev_cap = 0;
+    bool direct = false;
+    if (instances) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, instances) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            dev_out = at.devicePointer;
+            dev_cap = capacity;
+            direct = true;
+        } else {
+            cudaGetLastError();                       // a pageable pointer is not an error here
+            CK(d.inst[0].ensure(kArenaBytes));
+            dev_out = d.inst[0].p;
+            dev_cap = std::min(capacity, kArenaBytes / rec);
+        }
+        vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), nullptr, nullptr, d_cnt, d_off, nn);
+        m.out = static_cast<vx_instance *>(dev_out);
+        m.packed = packed ? 1 : 0;
+        m.capacity = dev_cap;
+        m.status = d.st();
+        TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
+    }
+    unsigned char *h_down = d.h_stage + 2048;
+    CK(cudaMemcpyAsync(h_down, d_off, down, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_down + down, d.st(), 4, cudaMemcpyDeviceToHost, s));
+    if (blocks_out) CK(cudaMemcpyAsync(blocks_out, d_blocks, n * VX_VOXELS, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));                     // the one wait
+    std::memcpy(offsets, h_down, off_bytes);
+    std::memcpy(counts, h_down + off_bytes, 4 * n);
+    uint32_t st = 0;
+    std::memcpy(&st, h_down + down, 4);
+    const uint64_t total = offsets[n];
+    if (total_out) *total_out = total;
+    if (!instances) return VX_OK;
+    if (total > capacity)
+        return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
+    if (st & VX_ST_OVERFLOW) {
+        // fits the caller's buffer but not the arena slice the speculative emit was given: sliced path
+        vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), nullptr, nullptr, d_cnt, d_off, nn);
+        RET(dev_stream_instances(d, m, offsets, nn, instances, packed));
+        return sync_dev(d);
+    }
+    if (!direct && total) {
+        CK(cudaMemcpyAsync(instances, dev_out, total * rec, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return VX_OK;
+}
+
 static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
                               const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, void *instances_v,
                               size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
@@ -709,6 +801,9 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
     RET(check_params(params, &p));
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t nd = ctx->devs.size();
+    if (n <= kShortList)
+        return gen_mesh_short(ctx, coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out, blocks_out,
+                              packed);
     const uint32_t nn = (uint32_t)n;
     std::vector<uint32_t> lo(nd), hi(nd);
     std::vector<std::vector<uint64_t>> loc(nd);     // device-local offsets

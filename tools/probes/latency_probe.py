@@ -26,3 +26,19 @@ for n in (1, 9, 81):
     for _ in range(200):
         ctx.fill(c, blocks=True)
     print("      vx_fill (blocks to host) %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))
+
+# the two-call shape of the reference: Chunk::new (vx_fill) then create_mesh (vx_mesh) with 4 adjacent chunks
+pos = voxb200.ChunkCoord3D(0, 0, 0)
+data = voxb200.Chunk.new(pos, ctx)
+adj = [voxb200.Chunk.new(voxb200.ChunkCoord3D(*c), ctx) for c in ((-1, 0, 0), (1, 0, 0), (0, 0, -1), (0, 0, 1))]
+for _ in range(20):
+    data.create_mesh(ctx, adj)
+t0 = time.perf_counter()
+for _ in range(200):
+    mesh = data.create_mesh(ctx, adj)
+print("Chunk.create_mesh with 4 adjacent chunks (vx_mesh, 5 x 32 KiB up): %.1f us, %d quads" % (
+    (time.perf_counter() - t0) / 200 * 1e6, mesh.instances_len))
+t0 = time.perf_counter()
+for _ in range(200):
+    voxb200.Chunk.new(pos, ctx)
+print("Chunk.new (vx_fill, 32 KiB down): %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))

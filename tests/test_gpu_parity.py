@@ -647,3 +647,45 @@ def test_short_list_path_pinned_and_pageable_outputs(ctx, vox, oracle):
         ctx.gen_mesh(_grid(0, 0, 2, 1), out=guard)
     assert e.value.code == vox._lib.VX_ERR_CAPACITY
     assert (guard == 0xAB).all()
+
+
+@pytest.mark.parametrize("n_side,masked", [((32, 32), False), ((37, 21), True), ((16, 32), True)])
+def test_large_device_batches_equal_the_host_api(ctx, vox, n_side, masked):
+    """vx_gen_mesh_device on batches of 512+ chunks (the bench's call): counts, offsets, blocks and instance bytes
+    equal the host-API result, repeated calls reuse the scratch, and a capacity one quad short only raises the
+    overflow flag (counts and offsets stay complete)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    coords = _grid(-7, 3, n_side[0], n_side[1])
+    n = len(coords)
+    assert n >= 512
+    rng = np.random.default_rng(n)
+    masks = rng.integers(0, 16, size=n).astype(np.uint8) if masked else None
+    want = ctx.gen_mesh(coords, nbr_mask=masks, blocks=True)                   # host API: one piece
+    st = torch.cuda.Stream(device=dev)
+    d_c = torch.from_numpy(coords).to(dev)
+    d_m = torch.from_numpy(masks).to(dev) if masked else None
+    cap = want.total + 5
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_inst = torch.zeros(cap * 17, dtype=torch.int32, device=dev)
+    d_blocks = torch.zeros(n * 32768, dtype=torch.uint8, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        ctx.gen_mesh_device(d_c.data_ptr(), n, d_counts.data_ptr(), d_off.data_ptr(), d_inst.data_ptr(), cap,
+                            nbr_mask_ptr=d_m.data_ptr() if masked else None, status_ptr=d_status.data_ptr(),
+                            blocks_ptr=d_blocks.data_ptr(), stream=st.cuda_stream)
+        st.synchronize()
+        assert int(d_status[0].item()) == 0
+        assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), want.counts)
+        assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want.offsets)
+        assert np.array_equal(d_blocks.cpu().numpy().reshape(n, 32768), want.blocks)
+        assert d_inst[:want.total * 17].cpu().numpy().view(np.uint8).tobytes() == want.instances.tobytes()
+        d_inst.zero_()
+    # capacity one quad short: overflow flagged, counts and offsets still complete
+    ctx.gen_mesh_device(d_c.data_ptr(), n, d_counts.data_ptr(), d_off.data_ptr(), d_inst.data_ptr(), want.total - 1,
+                        nbr_mask_ptr=d_m.data_ptr() if masked else None, status_ptr=d_status.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    assert int(d_status[0].item()) & 1
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want.offsets)

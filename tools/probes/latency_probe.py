@@ -42,3 +42,14 @@ t0 = time.perf_counter()
 for _ in range(200):
     voxb200.Chunk.new(pos, ctx)
 print("Chunk.new (vx_fill, 32 KiB down): %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))
+
+# Frustum::contains for one AABB, and the per-frame draw gate over ~80 meshes (world.rs:34-37)
+planes = np.random.default_rng(0).standard_normal((1, 6, 4)).astype(np.float32)
+for n in (1, 81, 4096):
+    c = np.random.default_rng(n).integers(-40, 40, size=(n, 3)).astype(np.int32)
+    for _ in range(20):
+        ctx.frustum_cull(planes, c)
+    t0 = time.perf_counter()
+    for _ in range(300):
+        ctx.frustum_cull(planes, c)
+    print("vx_frustum_cull, 1 frame x %d AABBs: %.1f us" % (n, (time.perf_counter() - t0) / 300 * 1e6))

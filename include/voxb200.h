@@ -126,7 +126,8 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
  * over a coordinate list.  nbr_mask: uint8[n], bit k set = neighbour k is
  * present (its blocks come from the same noise, wherever it is); NULL =
  * present iff the neighbour coordinate is in the list.  blocks_out optional.
- * Lists of up to 32 chunks (the reference's one-chunk-per-call shape) take a one-synchronisation path;
+ * Lists of up to 32 chunks (the reference's one-chunk-per-call shape) take a one-synchronisation path
+ * and run concurrently when several threads call on the same context (up to 8 at a time);
  * if `instances` is pinned host memory (vx_host_alloc) the kernels write it directly.  On
  * VX_ERR_CAPACITY nothing is written to `instances`; counts, offsets and total_out are valid. */
 int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,

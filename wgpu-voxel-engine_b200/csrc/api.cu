@@ -11,7 +11,9 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -76,6 +78,7 @@ struct DevBuf {
 
 constexpr size_t kArenaBytes = size_t(256) << 20;                      // per instance arena
 constexpr size_t kSliceBytes = size_t(256) << 20;                      // staging for fill / frustum outputs
+constexpr size_t kMaxLanes = 8;                                        // concurrent short-list calls per context
 constexpr size_t kShortList = 32;                                      // lists up to this long take the one-sync path
 constexpr size_t kStageBytes = 4096;                                   // >= kShortList * (12 + 1 + 4 + 8) + 8 + 16
 
@@ -140,6 +143,13 @@ struct TimerScope {
 struct vx_ctx {
     std::vector<Dev> devs;
     std::mutex mu;
+    // Lanes: extra scratch sets + streams on the GPU of devs[0], created on demand (at most kMaxLanes).  A
+    // short-list vx_gen_mesh call leases one instead of taking `mu`, so the reference's pool threads
+    // (chunk_builder.rs:80-84, one chunk per call on one shared handle) overlap on the GPU instead of queueing.
+    std::vector<std::unique_ptr<Dev>> lanes;
+    std::vector<char> lane_busy;
+    std::mutex lane_mu;
+    std::condition_variable lane_cv;
 };
 
 namespace {
@@ -306,6 +316,98 @@ void split_range(size_t n, size_t nd, size_t d, size_t align, uint32_t *lo, uint
     *hi = (uint32_t)h;
 }
 
+cudaError_t init_dev(Dev &d, int id)
+{
+    d.id = id;
+    cudaError_t e = cudaSetDevice(d.id);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.id);
+    if (e == cudaSuccess) e = vx_init_mesh_kernels();
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaEventCreateWithFlags(&d.emit_done[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.d2h_done[b], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = d.small.ensure(64);
+    if (e == cudaSuccess) e = cudaMemset(d.small.p, 0, 64);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_small, 64, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_stage, kStageBytes, cudaHostAllocPortable);
+    return e;
+}
+
+void destroy_dev(Dev &d)
+{
+    cudaSetDevice(d.id);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&d.coords, &d.mask8, &d.occ, &d.typ, &d.halo, &d.halo_items, &d.table, &d.nbr, &d.nbr_in,
+                      &d.counts, &d.offsets, &d.small, &d.blocks, &d.noise, &d.inst[0], &d.inst[1], &d.planes,
+                      &d.vis, &d.bits, &d.mesh_mask})
+        b->release();
+    if (d.h_small) cudaFreeHost(d.h_small);
+    if (d.h_stage) cudaFreeHost(d.h_stage);
+    for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
+    for (auto &ev : d.free_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (d.emit_done[b]) cudaEventDestroy(d.emit_done[b]);
+        if (d.d2h_done[b]) cudaEventDestroy(d.d2h_done[b]);
+    }
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy) cudaStreamDestroy(d.copy);
+    if (d.aux) cudaStreamDestroy(d.aux);
+    if (d.fork) cudaEventDestroy(d.fork);
+    if (d.join) cudaEventDestroy(d.join);
+}
+
+// Lease of one lane for the duration of a short-list call.
+struct LaneLease {
+    vx_ctx *ctx = nullptr;
+    int idx = -1;
+    Dev *d = nullptr;
+    cudaError_t err = cudaSuccess;
+    explicit LaneLease(vx_ctx *c) : ctx(c)
+    {
+        std::unique_lock<std::mutex> lk(ctx->lane_mu);
+        for (;;) {
+            for (size_t i = 0; i < ctx->lanes.size(); ++i)
+                if (!ctx->lane_busy[i]) {
+                    idx = (int)i;
+                    break;
+                }
+            if (idx >= 0) break;
+            if (ctx->lanes.size() < kMaxLanes) {
+                std::unique_ptr<Dev> nd(new Dev());
+                err = init_dev(*nd, ctx->devs[0].id);
+                if (err != cudaSuccess) {
+                    destroy_dev(*nd);
+                    return;
+                }
+                ctx->lanes.push_back(std::move(nd));
+                ctx->lane_busy.push_back(0);
+                idx = (int)ctx->lanes.size() - 1;
+                break;
+            }
+            ctx->lane_cv.wait(lk);
+        }
+        ctx->lane_busy[idx] = 1;
+        d = ctx->lanes[idx].get();
+    }
+    ~LaneLease()
+    {
+        if (idx < 0) return;
+        {
+            std::lock_guard<std::mutex> lk(ctx->lane_mu);
+            ctx->lane_busy[idx] = 0;
+        }
+        ctx->lane_cv.notify_one();
+    }
+};
+
 }  // namespace
 
 // ===========================================================================
@@ -355,24 +457,7 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
     vx_ctx *ctx = new vx_ctx();
     ctx->devs.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
-        Dev &d = ctx->devs[i];
-        d.id = ids[i];
-        cudaError_t e = cudaSetDevice(d.id);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, d.id);
-        if (e == cudaSuccess) e = vx_init_mesh_kernels();
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming);
-        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-            e = cudaEventCreateWithFlags(&d.emit_done[b], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.d2h_done[b], cudaEventDisableTiming);
-        }
-        if (e == cudaSuccess) e = d.small.ensure(64);
-        if (e == cudaSuccess) e = cudaMemset(d.small.p, 0, 64);
-        if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_small, 64, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaHostAlloc((void **)&d.h_stage, kStageBytes, cudaHostAllocPortable);
+        const cudaError_t e = init_dev(ctx->devs[i], ids[i]);
         if (e != cudaSuccess) {
             int r = cuda_fail(e, "context setup", __LINE__);
             vx_destroy(ctx);
@@ -386,30 +471,8 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
 void vx_destroy(vx_ctx *ctx)
 {
     if (!ctx) return;
-    for (Dev &d : ctx->devs) {
-        cudaSetDevice(d.id);
-        cudaDeviceSynchronize();
-        for (DevBuf *b : {&d.coords, &d.mask8, &d.occ, &d.typ, &d.halo, &d.halo_items, &d.table, &d.nbr, &d.nbr_in,
-                          &d.counts, &d.offsets, &d.small, &d.blocks, &d.noise, &d.inst[0], &d.inst[1], &d.planes,
-                          &d.vis, &d.bits, &d.mesh_mask})
-            b->release();
-        if (d.h_small) cudaFreeHost(d.h_small);
-        if (d.h_stage) cudaFreeHost(d.h_stage);
-        for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
-        for (auto &ev : d.free_events) {
-            cudaEventDestroy(ev.first);
-            cudaEventDestroy(ev.second);
-        }
-        for (int b = 0; b < 2; ++b) {
-            if (d.emit_done[b]) cudaEventDestroy(d.emit_done[b]);
-            if (d.d2h_done[b]) cudaEventDestroy(d.d2h_done[b]);
-        }
-        if (d.stream) cudaStreamDestroy(d.stream);
-        if (d.copy) cudaStreamDestroy(d.copy);
-        if (d.aux) cudaStreamDestroy(d.aux);
-        if (d.fork) cudaEventDestroy(d.fork);
-        if (d.join) cudaEventDestroy(d.join);
-    }
+    for (Dev &d : ctx->devs) destroy_dev(d);
+    for (auto &l : ctx->lanes) destroy_dev(*l);
     delete ctx;
 }
 
@@ -418,8 +481,11 @@ int vx_num_devices(const vx_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; 
 uint64_t vx_launch_count(const vx_ctx *ctx)
 {
     uint64_t t = 0;
-    if (ctx)
+    if (ctx) {
         for (const Dev &d : ctx->devs) t += d.launches;
+        std::lock_guard<std::mutex> lk(const_cast<vx_ctx *>(ctx)->lane_mu);
+        for (const auto &l : ctx->lanes) t += l->launches;
+    }
     return t;
 }
 
@@ -707,11 +773,10 @@ int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, cons
 // PCIe and no second copy or synchronisation exists at all; otherwise the instances go through the
 // arena and one more copy of exactly `total` records.
 // ---------------------------------------------------------------------------
-static int gen_mesh_short(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params &p,
+static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_noise_params &p,
                           const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, unsigned char *instances,
                           size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
 {
-    Dev &d = ctx->devs[0];
     const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
     const uint32_t nn = (uint32_t)n;
     CK(cudaSetDevice(d.id));
@@ -747,9 +812,11 @@ static int gen_mesh_short(vx_ctx *ctx, const int32_t *coords, size_t n, const vx
             direct = true;
         } else {
             cudaGetLastError();                       // a pageable pointer is not an error here
-            CK(d.inst[0].ensure(kArenaBytes));
+            // a lane's arena only has to hold this list (n <= kShortList chunks)
+            const size_t arena = std::min(kArenaBytes, n * (size_t)VX_MAX_QUADS_PER_CHUNK * rec);
+            CK(d.inst[0].ensure(arena));
             dev_out = d.inst[0].p;
-            dev_cap = std::min(capacity, kArenaBytes / rec);
+            dev_cap = std::min(capacity, arena / rec);
         }
         vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), nullptr, nullptr, d_cnt, d_off, nn);
         m.out = static_cast<vx_instance *>(dev_out);
@@ -799,11 +866,18 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
     if (n == 0) return VX_OK;
     vx_noise_params p;
     RET(check_params(params, &p));
+    if (n <= kShortList && !ctx->devs[0].timing) {
+        // concurrent callers each lease a lane (own scratch + streams); `mu` is not taken
+        LaneLease lease(ctx);
+        if (!lease.d) return cuda_fail(lease.err, "lane setup", __LINE__);
+        return gen_mesh_short(*lease.d, coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out,
+                              blocks_out, packed);
+    }
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t nd = ctx->devs.size();
     if (n <= kShortList)
-        return gen_mesh_short(ctx, coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out, blocks_out,
-                              packed);
+        return gen_mesh_short(ctx->devs[0], coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out,
+                              blocks_out, packed);
     const uint32_t nn = (uint32_t)n;
     std::vector<uint32_t> lo(nd), hi(nd);
     std::vector<std::vector<uint64_t>> loc(nd);     // device-local offsets

@@ -28,3 +28,21 @@ def run(T, own, reps=150):
 
 for T in (1, 4, 16):
     print("threads %2d: shared context %8.0f chunks/s   context per thread %8.0f chunks/s" % (T, run(T, False), run(T, True)))
+
+# the two-call form (Chunk::new then create_mesh with its 4 neighbours) from T threads on one shared context
+def run2(T, reps=60):
+    ctx = voxb200.Context(devices=[0])
+    def worker(t):
+        for r in range(reps):
+            pos = (t * 9 + r % 4, 0, r)
+            data = voxb200.Chunk.new(voxb200.ChunkCoord3D(*pos), ctx)
+            adj = [voxb200.Chunk.new(voxb200.ChunkCoord3D(pos[0] - 1, 0, pos[2]), ctx), None, None, None]
+            data.create_mesh(ctx, adj)
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    worker(0)
+    t0 = time.perf_counter()
+    for th in ths: th.start()
+    for th in ths: th.join()
+    return T * reps / (time.perf_counter() - t0)
+for T in (1, 4, 16):
+    print("two-call form, threads %2d on one shared context: %8.0f chunks/s (2 fills + 1 mesh each)" % (T, run2(T)))

@@ -408,6 +408,26 @@ struct LaneLease {
     }
 };
 
+// The Dev a host call runs on: a leased lane for short lists (concurrent callers overlap), else the
+// context's first device under the context lock.
+struct DevGuard {
+    std::unique_lock<std::mutex> lk;
+    std::unique_ptr<LaneLease> lease;
+    Dev *d = nullptr;
+    cudaError_t err = cudaSuccess;
+    DevGuard(vx_ctx *ctx, size_t n)
+    {
+        if (n <= kShortList && !ctx->devs[0].timing) {
+            lease.reset(new LaneLease(ctx));
+            d = lease->d;
+            err = lease->err;
+        } else {
+            lk = std::unique_lock<std::mutex>(ctx->mu);
+            d = &ctx->devs[0];
+        }
+    }
+};
+
 }  // namespace
 
 // ===========================================================================
@@ -556,12 +576,14 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
     if (n > (size_t)0x7ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
     vx_noise_params p;
     RET(check_params(params, &p));
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t nd = ctx->devs.size();
+    DevGuard guard(ctx, n);
+    if (!guard.d) return cuda_fail(guard.err, "lane setup", __LINE__);
+    const bool on_lane = guard.lease != nullptr;
+    const size_t nd = on_lane ? 1 : ctx->devs.size();
     const size_t per_chunk = VX_ROWS * 4 + (blocks_out ? VX_VOXELS : 0) + (noise_out ? VX_VOXELS * 4 : 0);
     const size_t slice = std::max<size_t>(1, kSliceBytes / per_chunk);
     for (size_t di = 0; di < nd; ++di) {
-        Dev &d = ctx->devs[di];
+        Dev &d = on_lane ? *guard.d : ctx->devs[di];
         uint32_t lo, hi;
         split_range(n, nd, di, 1, &lo, &hi);
         if (hi <= lo) continue;
@@ -597,7 +619,8 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
         }
         if (near_zero_out) CK(cudaMemcpyAsync(d.h_small + 2, d.near(), 8, cudaMemcpyDeviceToHost, d.stream));
     }
-    for (Dev &d : ctx->devs) {
+    for (size_t di = 0; di < nd; ++di) {
+        Dev &d = on_lane ? *guard.d : ctx->devs[di];
         RET(sync_dev(d));
         if (near_zero_out) {
             uint64_t v;
@@ -668,8 +691,9 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
     if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
     offsets[0] = 0;
     if (n == 0) return VX_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    Dev &d = ctx->devs[0];
+    DevGuard guard(ctx, n);
+    if (!guard.d) return cuda_fail(guard.err, "lane setup", __LINE__);
+    Dev &d = *guard.d;
     CK(cudaSetDevice(d.id));
     cudaStream_t s = d.stream;
     const uint32_t nn = (uint32_t)n;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VX_VERSION 100          /* 0.1.0 */
+#define VX_VERSION 110          /* 0.1.1: vx_noise_params.simplex_scale */
 #define VX_CHUNK 32
 #define VX_VOXELS 32768
 #define VX_ROWS 1024            /* occupancy words per chunk: row = y*32+z, bit = x */
@@ -62,7 +62,16 @@ typedef struct vx_noise_params {
     float gain;          /* 2.5  */
     float lacunarity;    /* 0.5  */
     int32_t octaves;     /* 3 (1..VX_MAX_OCTAVES) */
+    /* Factor on every simplex_3d value (one f32 multiply per octave sample, before the FBM combination).
+     * simdnoise normalises simplex_3d to [-1, 1] with 32.69587493801679 in its later 3.1.x sources; the
+     * FastNoiseSIMD-lineage code it grew from returns the raw sum (= 1.0f here, bit for bit).  The crate
+     * is not vendored with the reference (Cargo.lock:1802-1808), so which of the two 3.1.6 ships is
+     * settled by tools/simdnoise_golden/ on a machine with cargo; both are parity-tested against the
+     * oracle.  0 selects the default. */
+    float simplex_scale; /* 32.69587493801679 */
 } vx_noise_params;
+#define VX_SIMPLEX_SCALE_DEFAULT 32.69587493801679f
+#define VX_SIMPLEX_SCALE_RAW 1.0f
 
 /* renderer/instance.rs:1-6 InstanceRaw, #[repr(C)]: 16 f32 + u32 = 68 bytes.
  * t_matrix[c] is column c of Translation(pos) * Rotation(face) (quad.rs:47-54). */

@@ -22,7 +22,7 @@ LEFT, RIGHT, BACK, FRONT, DOWN, UP = range(6)
 
 class NoiseParams(C.Structure):
     _fields_ = [("seed", C.c_int32), ("freq", C.c_float), ("gain", C.c_float),
-                ("lacunarity", C.c_float), ("octaves", C.c_int32)]
+                ("lacunarity", C.c_float), ("octaves", C.c_int32), ("simplex_scale", C.c_float)]
 
 
 QUAD_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("face", "<u4"), ("tex", "<u4")])
@@ -54,7 +54,7 @@ def lib():
         L.vxo_simplex_3d.restype = C.c_float
         L.vxo_simplex_3d.argtypes = [C.c_float] * 3 + [C.c_int32]
         L.vxo_fbm_3d.restype = C.c_float
-        L.vxo_fbm_3d.argtypes = [C.c_float] * 5 + [C.c_int32, C.c_int32]
+        L.vxo_fbm_3d.argtypes = [C.c_float] * 5 + [C.c_int32, C.c_int32, C.c_float]
         L.vxo_noise_chunk.argtypes = [i32p, C.POINTER(NoiseParams), vp]
         L.vxo_noise_chunk_simd.argtypes = [i32p, C.POINTER(NoiseParams), vp]
         L.vxo_have_avx2.restype = C.c_int

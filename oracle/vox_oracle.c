@@ -35,6 +35,8 @@ static const float G33 = 3.0f / 6.0f - 1.0f;  /* -0.5   */
 #define X_PRIME 1619u
 #define Y_PRIME 31337u
 #define Z_PRIME 6971u
+/* (f32) 32.69587493801679: simplex_3d's normaliser in the later 3.1.x sources (vox_oracle.h) */
+#define VXO_SIMPLEX_SCALE 32.69587493801679f
 
 void vxo_default_params(vxo_noise_params *p)
 {
@@ -44,6 +46,7 @@ void vxo_default_params(vxo_noise_params *p)
     p->gain = 2.5f;
     p->lacunarity = 0.5f;
     p->octaves = 3;
+    p->simplex_scale = VXO_SIMPLEX_SCALE;
 }
 
 static inline uint32_t hash3d(int32_t seed, uint32_t i, uint32_t j, uint32_t k)
@@ -125,16 +128,18 @@ float vxo_simplex_3d(float x, float y, float z, int32_t seed)
     return p2 + v0;
 }
 
-float vxo_fbm_3d(float x, float y, float z, float lac, float gain, int32_t octaves, int32_t seed)
+float vxo_fbm_3d(float x, float y, float z, float lac, float gain, int32_t octaves, int32_t seed,
+                 float scale)
 {
+    /* simplex_3d returns `sum * scale` (scale = 1 leaves the sum untouched bit for bit) */
     float amp = 1.0f;
-    float result = vxo_simplex_3d(x, y, z, seed);
+    float result = vxo_simplex_3d(x, y, z, seed) * scale;
     for (int32_t o = 1; o < octaves; ++o) {
         x = x * lac;
         y = y * lac;
         z = z * lac;
         amp = amp * gain;
-        result = (vxo_simplex_3d(x, y, z, seed) * amp) + result;
+        result = ((vxo_simplex_3d(x, y, z, seed) * scale) * amp) + result;
     }
     return result;
 }
@@ -161,7 +166,7 @@ void vxo_noise_chunk(const int32_t coord[3], const vxo_noise_params *p, float *o
             for (int xx = 0; xx < VXO_CHUNK; ++xx) {
                 float x = sx + (float)xx;
                 out[idx++] = vxo_fbm_3d(x * p->freq, y * p->freq, z * p->freq,
-                                        p->lacunarity, p->gain, p->octaves, p->seed);
+                                        p->lacunarity, p->gain, p->octaves, p->seed, p->simplex_scale);
             }
         }
     }
@@ -269,7 +274,7 @@ AVX2 static void noise_chunk_avx2(const int32_t coord[3], const vxo_noise_params
     float sx, sy, sz;
     chunk_origin(coord, &sx, &sy, &sz);
     const __m256 freq = _mm256_set1_ps(p->freq), lac = _mm256_set1_ps(p->lacunarity),
-                 gain = _mm256_set1_ps(p->gain);
+                 gain = _mm256_set1_ps(p->gain), scale = _mm256_set1_ps(p->simplex_scale);
     float xa[8];
     for (int i = 0; i < 8; ++i) xa[i] = sx + (float)i;
     size_t idx = 0;
@@ -281,13 +286,13 @@ AVX2 static void noise_chunk_avx2(const int32_t coord[3], const vxo_noise_params
             for (int xx = 0; xx < VXO_CHUNK / 8; ++xx) {
                 __m256 fx = _mm256_mul_ps(x, freq), fy = _mm256_mul_ps(y, freq), fz = _mm256_mul_ps(z, freq);
                 __m256 amp = _mm256_set1_ps(1.0f);
-                __m256 r = simplex_3d_v(fx, fy, fz, p->seed);
+                __m256 r = _mm256_mul_ps(simplex_3d_v(fx, fy, fz, p->seed), scale);
                 for (int32_t o = 1; o < p->octaves; ++o) {
                     fx = _mm256_mul_ps(fx, lac);
                     fy = _mm256_mul_ps(fy, lac);
                     fz = _mm256_mul_ps(fz, lac);
                     amp = _mm256_mul_ps(amp, gain);
-                    r = _mm256_add_ps(_mm256_mul_ps(simplex_3d_v(fx, fy, fz, p->seed), amp), r);
+                    r = _mm256_add_ps(_mm256_mul_ps(_mm256_mul_ps(simplex_3d_v(fx, fy, fz, p->seed), scale), amp), r);
                 }
                 _mm256_storeu_ps(out + idx, r);
                 idx += 8;

@@ -44,6 +44,13 @@ typedef struct {
     float gain;         /* 2.5 */
     float lacunarity;   /* 0.5 */
     int32_t octaves;    /* 3 */
+    /* Factor applied to every simplex_3d value (one f32 multiply per octave sample) before the FBM
+     * combination.  simdnoise's later 3.1.x sources normalise simplex_3d to [-1, 1] with
+     * 32.69587493801679 ("scaling factor found by numerical optimization"); the FastNoiseSIMD-lineage
+     * sources it started from return the raw sum (scale 1).  Which of the two 3.1.6 ships cannot be
+     * checked here (crate not vendored): the default is the normalised form, 1.0f selects the raw
+     * one, and tools/simdnoise_golden/ is the recipe that settles it on a machine with cargo. */
+    float simplex_scale; /* 32.69587493801679 */
 } vxo_noise_params;
 
 /* quad.rs:7-11 before to_raw(): integer world position, face, texture layer */
@@ -62,8 +69,9 @@ typedef struct {
 void vxo_default_params(vxo_noise_params *p);
 
 /* simdnoise scalar restatement; exposed for unit tests */
-float vxo_simplex_3d(float x, float y, float z, int32_t seed);
-float vxo_fbm_3d(float x, float y, float z, float lac, float gain, int32_t octaves, int32_t seed);
+float vxo_simplex_3d(float x, float y, float z, int32_t seed);           /* raw sum, before the scale */
+float vxo_fbm_3d(float x, float y, float z, float lac, float gain, int32_t octaves, int32_t seed,
+                 float simplex_scale);
 
 /* perlin_noise.rs:5-22 -> simdnoise get_3d_noise; out[x + 32*z + 1024*y] */
 void vxo_noise_chunk(const int32_t coord[3], const vxo_noise_params *p, float *out);

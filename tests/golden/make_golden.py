@@ -24,6 +24,8 @@ F3 = f32(1.0) / f32(3.0)
 G3 = f32(1.0) / f32(6.0)
 G33 = f32(3.0) / f32(6.0) - f32(1.0)
 XP, YP, ZP = np.uint32(1619), np.uint32(31337), np.uint32(6971)
+# simplex_3d's normaliser in simdnoise's later 3.1.x sources; the "raw" records use 1.0 (SURVEY App. A form)
+SCALED = f32(32.69587493801679)
 
 
 def _hash(seed, i, j, k):
@@ -83,22 +85,22 @@ def simplex3(x, y, z, seed):
     return ((v3 + v2) + v1) + v0
 
 
-def noise_chunk(coord, seed=1, freq=0.09, gain=2.5, lac=0.5, octaves=3):
+def noise_chunk(coord, seed=1, freq=0.09, gain=2.5, lac=0.5, octaves=3, scale=SCALED):
     cx, cy, cz = (int(c) for c in coord)
     ar = np.arange(32, dtype=f32)
     sx = f32(np.int32(cx * 32)) + ar          # simdnoise x = engine x
     sy = f32(np.int32(cz * 32)) + ar          # simdnoise y = engine z
     sz = f32(np.int32(cy * 32)) + ar          # simdnoise z = engine y
     Z, Y, X = np.meshgrid(sz, sy, sx, indexing="ij")   # out[z][y][x] == engine idx
-    freq, gain, lac = f32(freq), f32(gain), f32(lac)
+    freq, gain, lac, scale = f32(freq), f32(gain), f32(lac), f32(scale)
     x, y, z = X * freq, Y * freq, Z * freq
     amp = f32(1.0)
     with np.errstate(over="ignore"):
-        r = simplex3(x, y, z, seed)
+        r = simplex3(x, y, z, seed) * scale
         for _ in range(1, octaves):
             x, y, z = x * lac, y * lac, z * lac
             amp = amp * gain
-            r = simplex3(x, y, z, seed) * amp + r
+            r = (simplex3(x, y, z, seed) * scale) * amp + r
     assert r.dtype == f32
     return r.reshape(-1)
 
@@ -131,13 +133,13 @@ def face_masks(solid, adj):
     return [left, right, back, front, down, up]
 
 
-def chunk_record(coord):
-    noise = noise_chunk(coord)
+def chunk_record(coord, scale=SCALED):
+    noise = noise_chunk(coord, scale=scale)
     occ = np.where(noise < 0, 0, 2).astype(np.uint8)
     solid = (occ != 2).reshape(32, 32, 32)
     cx, cy, cz = coord
     nbc = [(cx - 1, cy, cz), (cx + 1, cy, cz), (cx, cy, cz - 1), (cx, cy, cz + 1)]
-    adj = [(noise_chunk(c) < 0).reshape(32, 32, 32) for c in nbc]
+    adj = [(noise_chunk(c, scale=scale) < 0).reshape(32, 32, 32) for c in nbc]
     none = [int(m.sum()) for m in face_masks(solid, [None] * 4)]
     allf = [int(m.sum()) for m in face_masks(solid, adj)]
     # emission-order digest: for every emitted quad (y,z,x major; L,R,B,F,D,U)
@@ -281,7 +283,9 @@ def main():
     coords = [(0, 0, 0), (1, 0, 0), (-1, 0, -1), (511, 0, -512), (-16, 0, 15), (7, 1, -3), (0, -2, 0)]
     gold = {
         "about": "numpy restatement (tests/golden/make_golden.py); noise parity vs simdnoise 3.1.6 is UNPINNED",
-        "chunks": [chunk_record(c) for c in coords],
+        "simplex_scale": float(SCALED),
+        "chunks": [chunk_record(c) for c in coords],                      # default: simplex_3d normalised
+        "chunks_raw": [chunk_record(c, scale=1.0) for c in coords],       # simplex_scale = 1 (raw sum)
         "survey_app_a": SURVEY_APP_A,
         "rotations": rotations(),
         "frustum": frustum_fixture(),
@@ -290,7 +294,7 @@ def main():
     with open(path, "w") as fh:
         json.dump(gold, fh, indent=1)
     print("wrote", path)
-    for rec, ref in zip(gold["chunks"], SURVEY_APP_A):
+    for rec, ref in zip(gold["chunks_raw"], SURVEY_APP_A):
         for key in ("solid", "occ_crc32", "faces_none", "faces_all", "noise_1000"):
             status = "ok" if rec[key] == ref[key] else "MISMATCH"
             print(rec["coord"], key, rec[key], ref[key], status)

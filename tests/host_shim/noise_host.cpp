@@ -25,9 +25,14 @@ static inline float __saturatef(float v) { return v != v ? 0.0f : fminf(fmaxf(v,
 #include "../../wgpu-voxel-engine_b200/csrc/vx_noise.cuh"
 
 // same coordinate construction and hoisting as vx_fill_kernel (kernels_fill.cu)
+// simplex_scale of the following calls (vx_noise_params.simplex_scale); 1 = raw sum
+static float g_scale = 1.0f;
+extern "C" void shim_set_scale(float s) { g_scale = s; }
+
 extern "C" void shim_noise_chunk(const int32_t *c, int32_t seed, float freq, float gain, float lac, int oct,
                                  float *out)
 {
+    const float scale = g_scale;
     const float ox = (float)(int32_t)((uint32_t)c[0] * 32u);
     const float oy = (float)(int32_t)((uint32_t)c[2] * 32u);
     const float oz = (float)(int32_t)((uint32_t)c[1] * 32u);
@@ -36,10 +41,10 @@ extern "C" void shim_noise_chunk(const int32_t *c, int32_t seed, float freq, flo
             const float sx = ox + (float)lane, sy = oy + (float)zz;
             for (int y = 0; y < 32; ++y) {
                 float x = sx * freq, yy = sy * freq, z = (oz + (float)y) * freq, amp = 1.0f;
-                float r = vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed);
+                float r = vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed) * scale;
                 for (int o = 1; o < oct; ++o) {
                     x *= lac; yy *= lac; z *= lac; amp *= gain;
-                    r = vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed) * amp + r;
+                    r = (vxn_simplex3(x, yy, z, x + yy, (uint32_t)seed) * scale) * amp + r;
                 }
                 out[lane + 32 * zz + 1024 * y] = r;
             }
@@ -61,11 +66,17 @@ static void noise_chunk_sign(const int32_t *c, int32_t seed, float freq, float g
             const float4 *ll = lut + (lane & 7);
             for (int y = 0; y < 32; ++y) {
                 float x = sx * freq, yy = sy * freq, z = (oz + (float)y) * freq, amp = 1.0f;
-                float r = vxn_simplex3_sign<FUSED>(x, yy, z, x + yy, (uint32_t)seed, ll);
-                for (int o = 1; o < 3; ++o) {
-                    x *= lac; yy *= lac; z *= lac; amp *= gain;
-                    r = vxn_simplex3_sign<FUSED>(x, yy, z, x + yy, (uint32_t)seed, ll) * amp + r;
+                float sv[3], av[3];
+                for (int o = 0; o < 3; ++o) {
+                    if (o) { x *= lac; yy *= lac; z *= lac; amp *= gain; }
+                    sv[o] = vxn_simplex3_sign<FUSED>(x, yy, z, x + yy, (uint32_t)seed, ll);
+                    av[o] = amp;
                 }
+                float r;
+                if (FUSED)      // the kernels' fused combination: one product by fl(scale * amp) per octave
+                    r = fmaf(sv[0], g_scale, fmaf(sv[1], g_scale * av[1], sv[2] * (g_scale * av[2])));
+                else            // the reference's order: r = s0'; r = s1' * amp + r; ...   with s' = s * scale
+                    r = ((sv[2] * g_scale) * av[2]) + (((sv[1] * g_scale) * av[1]) + (sv[0] * g_scale));
                 out[lane + 32 * zz + 1024 * y] = r;
             }
         }
@@ -90,7 +101,7 @@ static void noise_chunk_x2(const int32_t *c, int32_t seed, float freq, float gai
     const float ox = (float)(int32_t)((uint32_t)c[0] * 32u);
     const float oy = (float)(int32_t)((uint32_t)c[2] * 32u);
     const float oz = (float)(int32_t)((uint32_t)c[1] * 32u);
-    const float amp1 = 1.0f * gain, amp2 = amp1 * gain;
+    const float amp1 = 1.0f * gain, amp2 = amp1 * gain, ka1 = g_scale * amp1, ka2 = g_scale * amp2;
     for (int zz = 0; zz < 32; ++zz)
         for (int lane = 0; lane < 32; ++lane) {
             const float sx = ox + (float)lane, sy = oy + (float)zz;
@@ -106,7 +117,7 @@ static void noise_chunk_x2(const int32_t *c, int32_t seed, float freq, float gai
                     const float2 s3 = vxn_simplex3_fused_x2(VX2(hx[2]), VX2(hy[2]), make_float2(za2, zb2), VX2(hxy[2]), (uint32_t)seed, ll);
                     const float2 s2 = vxn_simplex3_fused_x2(VX2(hx[1]), VX2(hy[1]), make_float2(za1, zb1), VX2(hxy[1]), (uint32_t)seed, ll);
                     const float2 s1 = vxn_simplex3_fused_x2(VX2(hx[0]), VX2(hy[0]), make_float2(za0, zb0), VX2(hxy[0]), (uint32_t)seed, ll);
-                    const float2 r = __fadd2_rn(__ffma2_rn(s2, VX2(amp1), __fmul2_rn(s3, VX2(amp2))), s1);   // kernel's fused order
+                    const float2 r = __ffma2_rn(s1, VX2(g_scale), __ffma2_rn(s2, VX2(ka1), __fmul2_rn(s3, VX2(ka2))));   // kernel's fused order
                     out[lane + 32 * zz + 1024 * ya] = r.x;
                     out[lane + 32 * zz + 1024 * yb] = r.y;
                 }
@@ -120,7 +131,7 @@ static int noise_chunk_lattice(const int32_t *c, int32_t seed, float freq, float
     const float ox = (float)(int32_t)((uint32_t)c[0] * 32u);
     const float oy = (float)(int32_t)((uint32_t)c[2] * 32u);
     const float oz = (float)(int32_t)((uint32_t)c[1] * 32u);
-    const float amp1 = 1.0f * gain, amp2 = amp1 * gain;
+    const float amp1 = 1.0f * gain, amp2 = amp1 * gain, ka1 = g_scale * amp1, ka2 = g_scale * amp2;
     static char tab[3][VXL_TAB_BYTES];
     int unfit = 0;
     for (int zblk = 0; zblk < 8; ++zblk) {
@@ -169,7 +180,7 @@ static int noise_chunk_lattice(const int32_t *c, int32_t seed, float freq, float
                         const float2 s3 = vxn_simplex3_lattice_x2(VX2(hx[2]), VX2(hy[2]), make_float2(za2, zb2), VX2(hxy[2]), og[2], tab[2]);
                         const float2 s2 = vxn_simplex3_lattice_x2(VX2(hx[1]), VX2(hy[1]), make_float2(za1, zb1), VX2(hxy[1]), og[1], tab[1]);
                         const float2 s1 = vxn_simplex3_lattice_x2(VX2(hx[0]), VX2(hy[0]), make_float2(za0, zb0), VX2(hxy[0]), og[0], tab[0]);
-                        const float2 r = __fadd2_rn(__ffma2_rn(s2, VX2(amp1), __fmul2_rn(s3, VX2(amp2))), s1);
+                        const float2 r = __ffma2_rn(s1, VX2(g_scale), __ffma2_rn(s2, VX2(ka1), __fmul2_rn(s3, VX2(ka2))));
                         out[lane + 32 * zz + 1024 * ya] = r.x;
                         out[lane + 32 * zz + 1024 * yb] = r.y;
                     }
@@ -202,7 +213,8 @@ static void noise_chunk_x1(const int32_t *c, int32_t seed, float freq, float gai
                 const float s3 = vxn_simplex3_sign<FUSED>(x2, y2, z2, x2 + y2, (uint32_t)seed, ll);
                 const float s2 = vxn_simplex3_sign<FUSED>(x1, y1, z1, x1 + y1, (uint32_t)seed, ll);
                 const float s1 = vxn_simplex3_sign<FUSED>(x0, y0, z0, x0 + y0, (uint32_t)seed, ll);
-                out[lane + 32 * zz + 1024 * y] = FUSED ? (fmaf(s2, amp1, s3 * amp2) + s1) : (s3 * amp2 + (s2 * amp1 + s1));
+                out[lane + 32 * zz + 1024 * y] = FUSED ? fmaf(s1, g_scale, fmaf(s2, g_scale * amp1, s3 * (g_scale * amp2)))
+                                                       : ((s3 * g_scale) * amp2 + ((s2 * g_scale) * amp1 + (s1 * g_scale)));
             }
         }
 }

@@ -28,11 +28,16 @@ def test_header_symbols_exported(vox):
 
 def test_version_and_defaults(vox):
     L = vox._lib.lib()
-    assert L.vx_version() == 100
+    assert L.vx_version() == 110
     p = vox.default_noise_params()
     # perlin_noise.rs:14-18
     assert (p.seed, p.octaves) == (1, 3)
     assert np.float32(p.freq) == np.float32(0.09) and p.gain == 2.5 and p.lacunarity == 0.5
+    assert np.float32(p.simplex_scale) == np.float32(32.69587493801679)
+    # the Rust mirror of the struct has the same fields in the same order
+    rs = open(os.path.join(ROOT, "wgpu-voxel-engine_b200", "rust", "voxb200-sys", "src", "lib.rs")).read()
+    body = rs.split("pub struct vx_noise_params {")[1].split("}")[0]
+    assert re.findall(r"pub (\w+):", body) == [f for f, _ in type(p)._fields_]
 
 
 def test_instance_layout(vox):

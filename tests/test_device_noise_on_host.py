@@ -21,46 +21,59 @@ def shim(tmp_path_factory):
     L.shim_noise_chunk_sign.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.shim_noise_chunk_fused.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.shim_fused_err_ulps.restype = C.c_float
+    L.shim_set_scale.argtypes = [C.c_float]
     L.shim_noise_chunk_lattice.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
     for f in (L.shim_noise_chunk_x2, L.shim_noise_chunk_x1):
         f.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
-    return L
+    yield L
+
+
+SCALED = 32.69587493801679          # vx_noise_params.simplex_scale default; 1.0 = the raw sum
+
+
+@pytest.fixture(params=[1.0, SCALED], ids=["raw", "scaled"])
+def scale(request, shim):
+    shim.shim_set_scale(request.param)
+    yield request.param
+    shim.shim_set_scale(1.0)
 
 
 @pytest.mark.parametrize("coord", [(0, 0, 0), (-1, 0, -1), (511, 0, -512), (7, 1, -3), (100000, 3, -99999)])
-def test_device_noise_source_matches_oracle(shim, oracle, coord):
+def test_device_noise_source_matches_oracle(shim, oracle, coord, scale):
     c = np.array(coord, np.int32)
     out = np.empty(32768, np.float32)
     shim.shim_noise_chunk(c.ctypes.data, 1, 0.09, 2.5, 0.5, 3, out.ctypes.data)
-    want = oracle.noise_chunk(coord)
+    want = oracle.noise_chunk(coord, oracle.default_params(simplex_scale=scale))
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
-def test_device_noise_other_params(shim, oracle):
+def test_device_noise_other_params(shim, oracle, scale):
     c = np.array((3, -1, 4), np.int32)
     out = np.empty(32768, np.float32)
     shim.shim_noise_chunk(c.ctypes.data, 12345, 0.9, 1.7, 0.4, 5, out.ctypes.data)
-    want = oracle.noise_chunk((3, -1, 4), oracle.default_params(seed=12345, freq=0.9, gain=1.7, lacunarity=0.4, octaves=5))
+    want = oracle.noise_chunk((3, -1, 4), oracle.default_params(seed=12345, freq=0.9, gain=1.7, lacunarity=0.4, octaves=5,
+                                                                simplex_scale=scale))
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
 @pytest.mark.parametrize("coord,seed,gain,lac,freq", [((0, 0, 0), 1, 2.5, 0.5, 0.09), ((-1, 0, -1), 1, 2.5, 0.5, 0.09),
                                                        ((511, 0, -512), 1, 2.5, 0.5, 0.09), ((9, -3, 4), 77, -3.0, 0.7, 0.2),
                                                        ((100000, 3, -99999), 5, 1.0, 2.0, 0.03)])
-def test_sign_only_gradient_variant(shim, oracle, coord, seed, gain, lac, freq):
+def test_sign_only_gradient_variant(shim, oracle, coord, seed, gain, lac, freq, scale):
     """vxn_simplex3_sign (coefficient-table gradient on the FMA pipe) equals the exact noise in value;
     only the sign of a zero may differ, which `noise < 0` cannot see."""
     c = np.array(coord, np.int32)
     out = np.empty(32768, np.float32)
     shim.shim_noise_chunk_sign(c.ctypes.data, seed, freq, gain, lac, out.ctypes.data)
-    want = oracle.noise_chunk(coord, oracle.default_params(seed=seed, freq=freq, gain=gain, lacunarity=lac))
+    want = oracle.noise_chunk(coord, oracle.default_params(seed=seed, freq=freq, gain=gain, lacunarity=lac,
+                                                           simplex_scale=scale))
     assert np.array_equal(out, want)                       # value equality (+0 == -0)
     nz = want != 0
     assert np.array_equal(out.view(np.uint32)[nz], want.view(np.uint32)[nz])
     assert np.array_equal(out < 0, want < 0)
 
 
-def test_fused_evaluation_stays_inside_its_certified_bound(shim, oracle):
+def test_fused_evaluation_stays_inside_its_certified_bound(shim, oracle, scale):
     """The FMA evaluation used for sign decisions differs from the exact noise by far less than the
     margin the kernel demands before trusting it."""
     eps = 2.0 ** -24
@@ -71,10 +84,11 @@ def test_fused_evaluation_stays_inside_its_certified_bound(shim, oracle):
         c = np.array(coord, np.int32)
         out = np.empty(32768, np.float32)
         shim.shim_noise_chunk_fused(c.ctypes.data, 1, 0.09, 2.5, 0.5, out.ctypes.data)
-        want = oracle.noise_chunk(coord)
+        want = oracle.noise_chunk(coord, oracle.default_params(simplex_scale=scale))
         worst = max(worst, float(np.max(np.abs(out.astype(np.float64) - want.astype(np.float64)))))
     amps = 1 + 2.5 + 6.25
-    bound = (ulps * amps + 2 * amps) * eps           # per-octave bound x amplitudes + FBM roundings
+    # vx_launch_fill's err_margin / 3: raw-sum bound x |scale| x amplitudes + the combination's roundings
+    bound = (ulps * scale + 5 * max(1.0, 0.0306 * scale)) * amps * eps
     assert worst <= bound, (worst, bound)
     assert worst > 0                                  # it really is a different rounding sequence
     print("max |fused - exact| = %.3g, certified bound %.3g, kernel margin %.3g" % (worst, bound, 3 * bound))

@@ -12,30 +12,35 @@ def _neighbours(c):
 
 
 def test_survey_app_a_vectors(oracle, golden):
+    # SURVEY App. A restates the raw simplex sum: simplex_scale = 1
+    raw = oracle.default_params(simplex_scale=1.0)
     for ref in golden["survey_app_a"]:
         c = ref["coord"]
-        noise = oracle.noise_chunk(c)
+        noise = oracle.noise_chunk(c, raw)
         cubes = oracle.terrain_from_noise(noise)
         assert int((cubes != oracle.AIR).sum()) == ref["solid"]
         assert "%08x" % zlib.crc32(cubes.tobytes()) == ref["occ_crc32"]
         assert "%08x" % int(noise[1000:1001].view(np.uint32)[0]) == ref["noise_1000"]
         q = oracle.cull_unseen_triangles(c, cubes, None)
         assert np.bincount(q["face"], minlength=6).tolist() == ref["faces_none"]
-        adj = [oracle.generate_terrain(n) for n in _neighbours(c)]
+        adj = [oracle.generate_terrain(n, raw) for n in _neighbours(c)]
         q = oracle.cull_unseen_triangles(c, cubes, adj)
         assert np.bincount(q["face"], minlength=6).tolist() == ref["faces_all"]
 
 
-def test_numpy_golden_chunks(oracle, golden):
-    for rec in golden["chunks"]:
+@pytest.mark.parametrize("key,scale", [("chunks", None), ("chunks_raw", 1.0)])
+def test_numpy_golden_chunks(oracle, golden, key, scale):
+    prm = oracle.default_params() if scale is None else oracle.default_params(simplex_scale=scale)
+    assert np.float32(oracle.default_params().simplex_scale) == np.float32(golden["simplex_scale"])
+    for rec in golden[key]:
         c = rec["coord"]
-        noise = oracle.noise_chunk(c)
+        noise = oracle.noise_chunk(c, prm)
         assert ["%08x" % int(v) for v in noise[::997].view(np.uint32)] == rec["noise_sample_997"]
         assert int((np.abs(noise) <= np.float32(1e-6)).sum()) == rec["near_zero_1e-6"]
         cubes = oracle.terrain_from_noise(noise)
         assert "%08x" % zlib.crc32(cubes.tobytes()) == rec["occ_crc32"]
         assert int((cubes != oracle.AIR).sum()) == rec["solid"]
-        adj = [oracle.generate_terrain(n) for n in _neighbours(c)]
+        adj = [oracle.generate_terrain(n, prm) for n in _neighbours(c)]
         q = oracle.cull_unseen_triangles(c, cubes, adj)
         assert np.bincount(q["face"], minlength=6).tolist() == rec["faces_all"]
         # emission order: (y,z,x)-major then L,R,B,F,D,U  (chunk.rs:65-69,77-240)
@@ -64,7 +69,12 @@ def test_noise_properties(oracle):
     n0 = oracle.noise_chunk((0, 0, 0))
     assert n0[0] == 0.0 and n0[1] == 0.0            # noise[0..2] exactly 0 -> AIR
     assert oracle.terrain_from_noise(n0)[0] == oracle.AIR
-    assert -0.35 < float(n0.min()) < float(n0.max()) < 0.35
+    assert -0.35 * 32.7 < float(n0.min()) < float(n0.max()) < 0.35 * 32.7
+    raw = oracle.noise_chunk((0, 0, 0), oracle.default_params(simplex_scale=1.0))
+    assert -0.35 < float(raw.min()) < float(raw.max()) < 0.35
+    # the normalised form is the raw form times 32.69587 up to the per-octave rounding
+    assert np.allclose(n0, raw * np.float32(32.69587493801679), rtol=1e-5, atol=1e-5)
+    assert (np.sign(n0) != np.sign(raw)).sum() <= 4      # only near-zero sums can flip
     # seed sensitivity and determinism
     p2 = oracle.default_params(seed=2)
     assert not np.array_equal(oracle.noise_chunk((0, 0, 0), p2), n0)
@@ -72,7 +82,7 @@ def test_noise_properties(oracle):
     # continuity across a chunk border: world-adjacent voxels differ only slightly
     n1 = oracle.noise_chunk((1, 0, 0)).reshape(32, 32, 32)
     d = np.abs(n0.reshape(32, 32, 32)[:, :, 31] - n1[:, :, 0])
-    assert float(d.max()) < 0.05
+    assert float(d.max()) < 0.05 * 32.7
     # octaves=1 equals plain simplex at freq-scaled coords
     p1 = oracle.default_params(octaves=1)
     n = oracle.noise_chunk((2, 0, 1), p1)
@@ -80,7 +90,7 @@ def test_noise_properties(oracle):
     f = np.float32(0.09)
     x, y, z = np.float32(64 + 5), np.float32(3), np.float32(32 + 7)     # engine (x,y,z) = (5,3,7)
     want = L.vxo_simplex_3d(x * f, z * f, y * f, 1)                    # simdnoise (x,y,z)=(x,z,y)
-    assert np.float32(want) == n[5 + 32 * 7 + 1024 * 3]
+    assert np.float32(want) * np.float32(p1.simplex_scale) == n[5 + 32 * 7 + 1024 * 3]
 
 
 def test_threshold_rule(oracle):

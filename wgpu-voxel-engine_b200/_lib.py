@@ -29,7 +29,7 @@ class VoxError(RuntimeError):
 class NoiseParams(C.Structure):
     """perlin_noise.rs:14-18"""
     _fields_ = [("seed", C.c_int32), ("freq", C.c_float), ("gain", C.c_float),
-                ("lacunarity", C.c_float), ("octaves", C.c_int32)]
+                ("lacunarity", C.c_float), ("octaves", C.c_int32), ("simplex_scale", C.c_float)]
 
 
 def build(force: bool = False) -> str:

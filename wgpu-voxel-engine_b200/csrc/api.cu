@@ -158,6 +158,7 @@ int check_params(const vx_noise_params *in, vx_noise_params *out)
 {
     if (in) *out = *in;
     else vx_default_noise_params(out);
+    if (out->simplex_scale == 0.0f) out->simplex_scale = VX_SIMPLEX_SCALE_DEFAULT;
     if (out->octaves < 1 || out->octaves > VX_MAX_OCTAVES)
         return fail(VX_ERR_BAD_ARG, "octaves must be in 1..%d (got %d)", VX_MAX_OCTAVES, out->octaves);
     return VX_OK;
@@ -456,6 +457,7 @@ void vx_default_noise_params(vx_noise_params *p)
     p->gain = 2.5f;
     p->lacunarity = 0.5f;
     p->octaves = 3;
+    p->simplex_scale = VX_SIMPLEX_SCALE_DEFAULT;
 }
 
 int vx_create(const int *devices, int n_devices, vx_ctx **out)

@@ -66,6 +66,9 @@ vx_fill_kernel(const vx_fill_args a)
 
     const int oct = (OCT > 0) ? OCT : a.p.octaves;
     const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    // every simplex_3d value is multiplied by the crate's normaliser before the FBM combination
+    // (vx_noise_params.simplex_scale; 1.0f reproduces the raw sum bit for bit)
+    const float scale = a.p.simplex_scale;
     const uint32_t seed = (uint32_t)a.p.seed;
 
     constexpr int kHoist = (OCT > 0) ? OCT : 1;
@@ -90,12 +93,12 @@ vx_fill_kernel(const vx_fill_args a)
 #pragma unroll 2
     for (uint32_t y = y_first; y < y_last; ++y) {
         float z = __fmul_rn(__fadd_rn(oz, (float)y), freq);
-        float r = vxn_simplex3(hx[0], hy[0], z, hxy[0], seed);
+        float r = __fmul_rn(vxn_simplex3(hx[0], hy[0], z, hxy[0], seed), scale);
         if (OCT > 0) {
 #pragma unroll
             for (int o = 1; o < kHoist; ++o) {
                 z = __fmul_rn(z, lac);
-                r = __fadd_rn(__fmul_rn(vxn_simplex3(hx[o], hy[o], z, hxy[o], seed), hamp[o]), r);
+                r = __fadd_rn(__fmul_rn(__fmul_rn(vxn_simplex3(hx[o], hy[o], z, hxy[o], seed), scale), hamp[o]), r);
             }
         } else {
             float x = hx[0], yy = hy[0], amp = 1.0f;
@@ -104,7 +107,7 @@ vx_fill_kernel(const vx_fill_args a)
                 yy = __fmul_rn(yy, lac);
                 z = __fmul_rn(z, lac);
                 amp = __fmul_rn(amp, gain);
-                r = __fadd_rn(__fmul_rn(vxn_simplex3(x, yy, z, __fadd_rn(x, yy), seed), amp), r);
+                r = __fadd_rn(__fmul_rn(__fmul_rn(vxn_simplex3(x, yy, z, __fadd_rn(x, yy), seed), scale), amp), r);
             }
         }
         // chunk.rs:38: noise < 0. -> GRASS, else AIR (+-0 and NaN are AIR)
@@ -191,7 +194,7 @@ vx_fill_brick2_kernel(const vx_fill_args a)
     const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
     const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
     const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
-    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain, scale = a.p.simplex_scale;
     const uint32_t seed = (uint32_t)a.p.seed;
 
     // two voxels per thread: (y, y + 2) of one (x, z) column -> the x / z terms are broadcast pairs
@@ -207,6 +210,8 @@ vx_fill_brick2_kernel(const vx_fill_args a)
         }
     }
     const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+    // fused path: one product by (scale * amplitude) instead of the exact path's two roundings (covered by errm)
+    const float ka1 = __fmul_rn(scale, amp1), ka2 = __fmul_rn(scale, amp2);
     const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
     const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
 
@@ -222,19 +227,19 @@ vx_fill_brick2_kernel(const vx_fill_args a)
         const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
         // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
         bool solid_a, solid_b, certain;
-        const float2 u = __fmul2_rn(vxn_simplex3_fused_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], seed, lut_lane), VX2(amp2));
+        const float2 u = __fmul2_rn(vxn_simplex3_fused_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], seed, lut_lane), VX2(ka2));
         if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
             solid_a = u.x < 0.0f;
             solid_b = u.y < 0.0f;
             certain = true;
         } else {
-            const float2 ut = __ffma2_rn(vxn_simplex3_fused_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], seed, lut_lane), VX2(amp1), u);
+            const float2 ut = __ffma2_rn(vxn_simplex3_fused_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], seed, lut_lane), VX2(ka1), u);
             if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
                 solid_a = ut.x < 0.0f;
                 solid_b = ut.y < 0.0f;
                 certain = true;
             } else {
-                const float2 r = __fadd2_rn(ut, vxn_simplex3_fused_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], seed, lut_lane));
+                const float2 r = __ffma2_rn(vxn_simplex3_fused_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], seed, lut_lane), VX2(scale), ut);
                 solid_a = r.x < 0.0f;
                 solid_b = r.y < 0.0f;
                 certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;
@@ -246,9 +251,9 @@ vx_fill_brick2_kernel(const vx_fill_args a)
 #pragma unroll 1
             for (int e = 0; e < 2; ++e) {
                 const float q0 = e ? zb0 : za0, q1 = e ? zb1 : za1, q2 = e ? zb2 : za2;
-                const float ue = __fmul_rn(vxn_simplex3_sign<false>(hx[2].x, hy[2].x, q2, hxy[2].x, seed, lut_lane), amp2);
-                const float te = __fmul_rn(vxn_simplex3_sign<false>(hx[1].x, hy[1].x, q1, hxy[1].x, seed, lut_lane), amp1);
-                const float s1 = vxn_simplex3_sign<false>(hx[0].x, hy[0].x, q0, hxy[0].x, seed, lut_lane);
+                const float ue = __fmul_rn(__fmul_rn(vxn_simplex3_sign<false>(hx[2].x, hy[2].x, q2, hxy[2].x, seed, lut_lane), scale), amp2);
+                const float te = __fmul_rn(__fmul_rn(vxn_simplex3_sign<false>(hx[1].x, hy[1].x, q1, hxy[1].x, seed, lut_lane), scale), amp1);
+                const float s1 = __fmul_rn(vxn_simplex3_sign<false>(hx[0].x, hy[0].x, q0, hxy[0].x, seed, lut_lane), scale);
                 const bool sol = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
                 if (e) solid_b = sol; else solid_a = sol;
             }
@@ -297,7 +302,7 @@ vx_fill_brick2_kernel(const vx_fill_args a)
 // frequencies or coordinates beyond f32 resolution).
 // ---------------------------------------------------------------------------
 __device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float oz, uint32_t yy, uint32_t lane,
-                                                      float freq, float lac, float gain, uint32_t seed)
+                                                      float freq, float lac, float gain, float scale, uint32_t seed)
 {
     const float x0 = __fmul_rn(sx, freq), y0 = __fmul_rn(sy, freq);
     const float x1 = __fmul_rn(x0, lac), y1 = __fmul_rn(y0, lac);
@@ -308,9 +313,9 @@ __device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float 
     for (uint32_t it = 0; it < 16u; ++it) {
         const float z0 = __fmul_rn(__fadd_rn(oz, (float)(2u * it + yy)), freq);
         const float z1 = __fmul_rn(z0, lac), z2 = __fmul_rn(z1, lac);
-        float r = vxn_simplex3(x0, y0, z0, __fadd_rn(x0, y0), seed);
-        r = __fadd_rn(__fmul_rn(vxn_simplex3(x1, y1, z1, __fadd_rn(x1, y1), seed), amp1), r);
-        r = __fadd_rn(__fmul_rn(vxn_simplex3(x2, y2, z2, __fadd_rn(x2, y2), seed), amp2), r);
+        float r = __fmul_rn(vxn_simplex3(x0, y0, z0, __fadd_rn(x0, y0), seed), scale);
+        r = __fadd_rn(__fmul_rn(__fmul_rn(vxn_simplex3(x1, y1, z1, __fadd_rn(x1, y1), seed), scale), amp1), r);
+        r = __fadd_rn(__fmul_rn(__fmul_rn(vxn_simplex3(x2, y2, z2, __fadd_rn(x2, y2), seed), scale), amp2), r);
         const uint32_t word = __ballot_sync(VX_FULL, r < 0.0f);
         if (lane == it) my_word = word;
     }
@@ -332,7 +337,7 @@ vx_fill_lattice_kernel(const vx_fill_args a)
     const float ox = (float)(int32_t)((uint32_t)cx * 32u);
     const float oy = (float)(int32_t)((uint32_t)cz * 32u);
     const float oz = (float)(int32_t)((uint32_t)cy * 32u);
-    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain;
+    const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain, scale = a.p.simplex_scale;
     const uint32_t seed = (uint32_t)a.p.seed;
 
     // ---- index box of this CTA's 32 x 4 x 32 voxels, per octave: floor values at the 8 corners
@@ -373,7 +378,7 @@ vx_fill_lattice_kernel(const vx_fill_args a)
     const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
     uint32_t my_word = 0;
     if (!fit) {
-        my_word = vx_brick_exact_steps(sx, sy, oz, yy, lane, freq, lac, gain, seed);
+        my_word = vx_brick_exact_steps(sx, sy, oz, yy, lane, freq, lac, gain, scale, seed);
     } else {
         // ---- hash every lattice point of the three boxes once (+1 per axis for the far corners)
 #pragma unroll 1
@@ -404,6 +409,8 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             }
         }
         const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+        // fused path: one product by (scale * amplitude) instead of the exact path's two roundings (covered by errm)
+        const float ka1 = __fmul_rn(scale, amp1), ka2 = __fmul_rn(scale, amp2);
         const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
         const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
 #pragma unroll 1
@@ -415,19 +422,19 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
             // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
             bool solid_a, solid_b, certain;
-            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], s_og[2], 0), VX2(amp2));
+            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], s_og[2], 0), VX2(ka2));
             if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
                 solid_a = u.x < 0.0f;
                 solid_b = u.y < 0.0f;
                 certain = true;
             } else {
-                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], s_og[1], 0), VX2(amp1), u);
+                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], s_og[1], 0), VX2(ka1), u);
                 if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
                     solid_a = ut.x < 0.0f;
                     solid_b = ut.y < 0.0f;
                     certain = true;
                 } else {
-                    const float2 r = __fadd2_rn(ut, vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], s_og[0], 0));
+                    const float2 r = __ffma2_rn(vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], s_og[0], 0), VX2(scale), ut);
                     solid_a = r.x < 0.0f;
                     solid_b = r.y < 0.0f;
                     certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;
@@ -439,9 +446,9 @@ vx_fill_lattice_kernel(const vx_fill_args a)
 #pragma unroll 1
                 for (int e = 0; e < 2; ++e) {
                     const float q0 = e ? zb0 : za0, q1 = e ? zb1 : za1, q2 = e ? zb2 : za2;
-                    const float ue = __fmul_rn(vxn_simplex3(hx[2].x, hy[2].x, q2, hxy[2].x, seed), amp2);
-                    const float te = __fmul_rn(vxn_simplex3(hx[1].x, hy[1].x, q1, hxy[1].x, seed), amp1);
-                    const float s1 = vxn_simplex3(hx[0].x, hy[0].x, q0, hxy[0].x, seed);
+                    const float ue = __fmul_rn(__fmul_rn(vxn_simplex3(hx[2].x, hy[2].x, q2, hxy[2].x, seed), scale), amp2);
+                    const float te = __fmul_rn(__fmul_rn(vxn_simplex3(hx[1].x, hy[1].x, q1, hxy[1].x, seed), scale), amp1);
+                    const float s1 = __fmul_rn(vxn_simplex3(hx[0].x, hy[0].x, q0, hxy[0].x, seed), scale);
                     const bool sol = __fadd_rn(ue, __fadd_rn(te, s1)) < 0.0f;
                     if (e) solid_b = sol; else solid_a = sol;
                 }
@@ -523,18 +530,23 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
     // (the coefficient-table gradient multiplies by 0, so coordinates must stay finite:
     //  |world * freq * lac^k| <= 2^31 * |freq| * max(1, lac^2) must not overflow f32)
     const float reach = 2147483648.0f * fabsf(a.p.freq) * fmaxf(1.0f, a.p.lacunarity * a.p.lacunarity);
+    const float ks = fabsf(a.p.simplex_scale);
     const bool tame = isfinite(reach) && reach < 1e30f && isfinite(a.p.gain) && isfinite(a.p.freq) &&
-                      isfinite(a.p.lacunarity);      // NaN / inf parameters: the exact kernel reproduces them as is
+                      isfinite(a.p.lacunarity) && isfinite(ks) && ks >= 1e-3f && ks <= 1e3f;
+    // NaN / inf / extreme parameters: the exact kernel reproduces them as is
     if (!halo_mode && a.p.octaves == 3 && !a.noise && !a.near_zero && tame) {
         vx_fill_args b = a;
-        // |simplex_3d| <= 0.030585; 0.0306 plus a relative slack far above the f32 rounding of u, t, u+t
+        // |raw simplex sum| <= 0.030585, so |simplex_3d| <= 0.0306 |scale|; plus a relative slack far above
+        // the f32 rounding of u, t, u+t
         const float g1 = fabsf(a.p.gain), g2 = fabsf(a.p.gain * a.p.gain);
         const float slack = 1.0f + 1e-5f * (1.0f + g1 + g2);
-        b.thr1 = 0.0306f * slack;
-        b.thr2 = 0.0306f * (1.0f + g1) * slack;
-        // |fused - exact| <= VXN_FUSED_ERR_ULPS * 2^-24 per octave value, times the
-        // octave amplitudes, plus the roundings of the FBM combination; x3 slack on top.
-        b.err_margin = 3.0f * (VXN_FUSED_ERR_ULPS * (1.0f + g1 + g2) + 2.0f * (1.0f + g1 + g2)) * 5.9604645e-8f;
+        b.thr1 = 0.0306f * ks * slack;
+        b.thr2 = 0.0306f * ks * (1.0f + g1) * slack;
+        // |fused - exact| of the raw sum <= VXN_FUSED_ERR_ULPS * 2^-24, times |scale| and the
+        // octave amplitudes; the fused path's single product by fl(scale * amp) against the exact path's
+        // two roundings, the final rounding of each term (all relative 2^-24 of |term| <= 1.0005 amp) and
+        // the two FBM additions add 5 * 2^-24 per unit amplitude; x3 slack on top.
+        b.err_margin = 3.0f * (VXN_FUSED_ERR_ULPS * ks + 5.0f * fmaxf(1.0f, 0.0306f * ks)) * (1.0f + g1 + g2) * 5.9604645e-8f;
         const uint32_t n_items = a.max_units / 32u;
         // lattice tables hold 8 points per axis: a 32-voxel edge spans <= 52.7 * |f_k| cells in the skewed
         // index (x + (x + y + z) / 3), so |f_k| <= 0.1 fits with room for rounding; CTAs that still do

@@ -29,6 +29,8 @@ pub struct vx_noise_params {
     pub gain: f32,
     pub lacunarity: f32,
     pub octaves: i32,
+    /// factor on every `simplex_3d` value; 32.69587493801679 (default) or 1.0 (raw sum), see voxb200.h
+    pub simplex_scale: f32,
 }
 
 /// renderer/instance.rs:1-6 `InstanceRaw` (68 bytes, `#[repr(C)]`) -- same layout, so a

@@ -16,8 +16,12 @@
  *   - all outputs are caller-allocated; the library never frees caller memory.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails
  *     with VX_ERR_NO_DEVICE.
- *   - calls on one context are serialised (thread-safe); use one context per
- *     calling thread / GPU for concurrency.
+ *   - every entry point is thread-safe.  Batch calls (more than 32 chunks) and all *_device calls on one
+ *     context are serialised by the context lock; short vx_fill / vx_mesh / vx_gen_mesh calls (<= 32
+ *     chunks, the reference's one-chunk-per-call shape) instead lease one of up to 8 scratch lanes (own
+ *     buffers and streams on the context's first GPU) and run concurrently -- a ninth concurrent caller
+ *     waits for a lane.  vx_sync covers the context's own streams, not the lanes (a lane call has
+ *     finished when it returns).  Use one context per GPU, or one multi-GPU context.
  *   - chunk edge is fixed at 32 (world.rs:21); voxel index inside a chunk is
  *     idx = x + 32*z + 1024*y (chunk.rs:38,70); chunk -> world is a wrapping
  *     i32 multiply by 32 (coordinate.rs:60-65, release-build semantics).
@@ -124,6 +128,7 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
  * instances[capacity] in list order, each chunk's quads in the reference's
  * emission order ((y,z,x)-major, then LEFT,RIGHT,BACK,FRONT,DOWN,UP).
  * instances may be NULL (count only).  total_out receives offsets[n].
+ * An nbr_idx entry >= n is VX_ERR_BAD_ARG (checked before anything is enqueued).
  * (Runs on the context's first GPU: the call is PCIe-bound on the 32 KiB/chunk upload.) */
 int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
             const int32_t *nbr_idx, const uint8_t *mesh_mask,
@@ -181,7 +186,7 @@ int vx_frustum_cull_bits(vx_ctx *ctx, const float *planes, size_t n_frames,
  * stream -- pass cudaStreamLegacy / cudaStreamPerThread to name a default
  * stream explicitly) and the call returns without synchronising.  Capacity overflow cannot be
  * reported synchronously: status[0] (device uint32, optional) gets bit 0 set,
- * bit 1 = bad block id.  Scratch lives in the context and is valid until the
+ * bit 1 = bad block id, bit 2 = an nbr_idx entry >= n (treated as None).  Scratch lives in the context and is valid until the
  * next call on it. */
 int vx_fill_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
                    uint8_t *blocks_out, float *noise_out, uint32_t *occupancy_out,
@@ -198,6 +203,13 @@ int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_no
 int vx_frustum_cull_device(vx_ctx *ctx, const float *planes, size_t n_frames,
                            const int32_t *coords, size_t n, uint8_t *visible, uint32_t *bits,
                            void *stream);
+/* Emits the instances of the LAST vx_gen_mesh_device / vx_mesh_device batch of this context again (its
+ * occupancy planes and neighbour table are still in the context's scratch; counts / offsets are the
+ * arrays that call filled).  For a renderer that lost or re-sized its instance buffer: ChunkMesh::new
+ * (chunk.rs:254-266) without a new Chunk::new.  bench.py also uses it to time the emit kernel over
+ * back-to-back launches. */
+int vx_emit_again_device(vx_ctx *ctx, const int32_t *coords, size_t n, uint32_t *counts, uint64_t *offsets,
+                         vx_instance *instances, size_t capacity, uint32_t *status, void *stream);
 /* block until everything enqueued by this context has finished */
 int vx_sync(vx_ctx *ctx);
 

@@ -689,3 +689,125 @@ def test_large_device_batches_equal_the_host_api(ctx, vox, n_side, masked):
     st.synchronize()
     assert int(d_status[0].item()) & 1
     assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want.offsets)
+
+
+# ---- round 2: full-size streams, the 1024 x 1024 region, caves through the fused call, both noise scales -----
+def test_gen_mesh_ring_32x32_full_stream_equals_oracle(ctx, oracle):
+    """configs[1] at full size, everything compared: 1024 chunks, ~4.7 M instances = 321 MB, byte for byte."""
+    coords = _grid(-16, -16, 32, 32)
+    got = ctx.gen_mesh(coords, blocks=True)
+    want = oracle.gen_mesh_batch(coords, want_cubes=True)
+    assert np.array_equal(got.blocks, want["cubes"])
+    assert np.array_equal(got.counts, want["counts"]) and np.array_equal(got.offsets, want["offsets"])
+    assert got.total == want["total"] > 4_000_000
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+
+
+def test_region_1024_samples_equal_oracle(ctx, oracle):
+    """configs[2]: chunks sampled from the 1024 x 1024 region -- the four corners (+-512), both rows of every
+    band border of the 8-GPU sharding, 200 random ones -- meshed with the region's presence masks (neighbours
+    outside the list are halo slabs) equal the oracle in counts and instance bytes."""
+    import bench
+    R, h = 1024, 512
+    idx = bench.sample_indices(R, 8, extra=200, seed=3)
+    assert len(idx) >= 256
+    sc = np.stack([(idx % R) - h, np.zeros(len(idx), np.int64), (idx // R) - h], axis=1).astype(np.int32)
+    sm = ((sc[:, 0] > -h) * 1 + (sc[:, 0] < h - 1) * 2 + (sc[:, 2] > -h) * 4 + (sc[:, 2] < h - 1) * 8).astype(np.uint8)
+    assert {0b1010, 0b1001, 0b0110, 0b0101} <= set(sm.tolist())          # the four corner masks occur
+    o_counts, o_off, o_inst = bench.oracle_with_halo(sc, sm)
+    got = ctx.gen_mesh(sc, nbr_mask=sm)
+    assert np.array_equal(got.counts, o_counts) and np.array_equal(got.offsets, o_off)
+    assert _canon(got.instances).tobytes() == _canon(o_inst).tobytes()
+    # and the same rows inside a full 8192-chunk batch of the region (the bench's call shape): band border row
+    z0 = bench.band_rows(3, 8, R)[0]
+    c, m = bench.region_rows(z0 - 4, z0 + 4, R)
+    big = ctx.gen_mesh(c, nbr_mask=m, instances=False)
+    pick = np.arange(0, len(c), 61)
+    pc, _, _ = bench.oracle_with_halo(c[pick], m[pick])
+    assert np.array_equal(big.counts[pick], pc)
+
+
+def test_caves_through_gen_mesh(ctx, oracle, vox):
+    """configs[4] 'caves' (freq 0.9, one octave: ~50 % solid, ~10x the terrain's quads) through the FUSED call,
+    not only through vx_fill: blocks, counts and the instance stream equal the oracle."""
+    p = vox.default_noise_params(freq=0.9, octaves=1)
+    po = oracle.default_params(freq=0.9, octaves=1)
+    coords = _grid(-2, 3, 4, 4)
+    got = ctx.gen_mesh(coords, params=p, blocks=True)
+    want = oracle.gen_mesh_batch(coords, params=po, want_cubes=True)
+    assert np.array_equal(got.blocks, want["cubes"])
+    assert np.array_equal(got.counts, want["counts"])
+    assert got.total > 16 * 30000                                        # dense: stresses compaction
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+    # with halo neighbours (present but outside the list)
+    m = np.full(len(coords), 15, np.uint8)
+    got2 = ctx.gen_mesh(coords[:3], params=p, nbr_mask=m[:3])
+    import bench
+    oc, oo, oi = _oracle_halo_params(oracle, coords[:3], m[:3], po)
+    assert np.array_equal(got2.counts, oc)
+    assert _canon(got2.instances).tobytes() == _canon(oi).tobytes()
+
+
+def _oracle_halo_params(oracle, coords, masks, params):
+    out_c, out_i = [], []
+    for c, m in zip(coords, masks):
+        cubes = oracle.generate_terrain(c, params)
+        adj = [oracle.generate_terrain(nc, params) if (m >> k) & 1 else None for k, nc in enumerate(_neighbours(c))]
+        inst = oracle.create_mesh(c, cubes, adj)
+        out_c.append(len(inst))
+        out_i.append(inst)
+    return np.array(out_c, np.uint32), None, np.concatenate(out_i)
+
+
+@pytest.mark.parametrize("scale", [1.0, 32.69587493801679, -7.5])
+def test_simplex_scale_variants(ctx, oracle, vox, scale):
+    """vx_noise_params.simplex_scale: the raw simplex sum (1.0), simdnoise's normalised form (default) and an
+    arbitrary factor -- noise bit-exact, fast (sign-only) blocks equal exact blocks, meshes equal the oracle."""
+    p = vox.default_noise_params(simplex_scale=scale)
+    po = oracle.default_params(simplex_scale=scale)
+    cs = [(0, 0, 0), (-5, 0, 9), (511, 0, -512), (100000, 3, -99999)]
+    res = ctx.fill(cs, params=p, noise=True)
+    for i, c in enumerate(cs):
+        want = oracle.noise_chunk(c, po)
+        assert np.array_equal(res["noise"][i].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(res["blocks"][i], oracle.terrain_from_noise(want))
+    coords = _grid(-8, -8, 16, 16)
+    fast = ctx.fill(coords, params=p, blocks=True)["blocks"]
+    slow = ctx.fill(coords, params=p, blocks=True, noise=True)
+    assert np.array_equal(fast, slow["blocks"]) and np.array_equal(fast == 0, slow["noise"] < 0)
+    got = ctx.gen_mesh(coords[:40], params=p)
+    want = oracle.gen_mesh_batch(coords[:40], params=po)
+    assert np.array_equal(got.counts, want["counts"])
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+    if scale > 0:
+        # a positive scale leaves almost every block alone; the few near-zero sums it re-rounds may flip
+        base = ctx.fill(coords, blocks=True)["blocks"]
+        assert (base != fast).mean() < 1e-4
+    zero = ctx.fill(cs[:1], params=vox.default_noise_params(simplex_scale=0.0), noise=True)      # 0 = default
+    assert np.array_equal(zero["noise"][0], ctx.fill(cs[:1], noise=True)["noise"][0])
+
+
+def test_emit_again_device(ctx, vox):
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    coords = _grid(-3, 5, 12, 9)
+    n = len(coords)
+    host = ctx.gen_mesh(coords)
+    d_coords = torch.from_numpy(coords).to(dev)
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    cap = host.total + 5
+    a = torch.zeros(cap * 17, dtype=torch.int32, device=dev)
+    b = torch.zeros(cap * 17, dtype=torch.int32, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with vox.Context() as c2:
+        c2.gen_mesh_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_off.data_ptr(), a.data_ptr(), cap,
+                           status_ptr=st.data_ptr(), stream=s.cuda_stream)
+        c2.emit_again_device(d_coords.data_ptr(), n, d_counts.data_ptr(), d_off.data_ptr(), b.data_ptr(), cap,
+                             status_ptr=st.data_ptr(), stream=s.cuda_stream)
+        s.synchronize()
+        assert int(st.item()) == 0 and torch.equal(a, b)
+        assert a[:host.total * 17].cpu().numpy().tobytes() == host.instances.tobytes()
+        with pytest.raises(vox.VoxError):
+            c2.emit_again_device(d_coords.data_ptr(), n - 1, d_counts.data_ptr(), d_off.data_ptr(), b.data_ptr(), cap)

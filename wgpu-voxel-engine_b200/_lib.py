@@ -71,6 +71,7 @@ SIGNATURES = {
     "vx_fill_device": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _vp]),
     "vx_mesh_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vx_gen_mesh_device": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "vx_emit_again_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vx_frustum_cull_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "vx_sync": (_i, [_vp]),
     "vx_measure_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),

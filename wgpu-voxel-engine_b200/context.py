@@ -252,6 +252,11 @@ class Context:
                                          nbr_mask_ptr, counts_ptr, offsets_ptr, inst_ptr, capacity, status_ptr,
                                          blocks_ptr, stream))
 
+    def emit_again_device(self, coords_ptr, n, counts_ptr, offsets_ptr, inst_ptr, capacity, status_ptr=None,
+                          stream=None):
+        check(self._L.vx_emit_again_device(self._h, coords_ptr, n, counts_ptr, offsets_ptr, inst_ptr, capacity,
+                                           status_ptr, stream))
+
     def frustum_cull_device(self, planes_ptr, n_frames, coords_ptr, n, visible_ptr=None, bits_ptr=None,
                             stream=None):
         check(self._L.vx_frustum_cull_device(self._h, planes_ptr, n_frames, coords_ptr, n, visible_ptr, bits_ptr,

@@ -9,6 +9,10 @@
 // Instances stream back through the two arenas (emit slice k+1 overlaps the
 // D2H of slice k).  There is no CPU compute path in this file.
 #include <algorithm>
+#include <atomic>
+#include <deque>
+#include <functional>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <condition_variable>
@@ -93,8 +97,10 @@ struct Dev {
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
     uint64_t launches = 0;
+    size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
+    bool last_typ = false;         // ... and whether it had a DIRT plane
     // optional per-kernel-class CUDA-event timing (vx_set_timing)
-    bool timing = false;
+    std::atomic<bool> timing{false};       // read by lane callers without the context lock
     struct Stamp { cudaEvent_t a, b; int kind; };
     std::vector<Stamp> stamps;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_events;
@@ -141,7 +147,7 @@ struct TimerScope {
 }  // namespace
 
 struct vx_ctx {
-    std::vector<Dev> devs;
+    std::deque<Dev> devs;          // (Dev holds an atomic: never copied or moved)
     std::mutex mu;
     // Lanes: extra scratch sets + streams on the GPU of devs[0], created on demand (at most kMaxLanes).  A
     // short-list vx_gen_mesh call leases one instead of taking `mu`, so the reference's pool threads
@@ -272,7 +278,9 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
     const size_t kArenaQuads = kArenaBytes / rec;
     unsigned char *h_out = static_cast<unsigned char *>(h_out_v);
     m.packed = packed ? 1 : 0;
-    CK(d.inst[0].ensure(kArenaBytes));
+    // a list whose instances fit one arena only needs that much of it (lanes serve one-chunk calls)
+    const size_t need = std::min(kArenaBytes, std::max<size_t>((size_t)h_off[n] * rec, 256));
+    CK(d.inst[0].ensure(need));
     if (h_off[n] > kArenaQuads) CK(d.inst[1].ensure(kArenaBytes));
     uint32_t a = 0;
     int k = 0;
@@ -284,7 +292,7 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
             const int buf = k & 1;
             CK(cudaStreamWaitEvent(d.stream, d.d2h_done[buf], 0));      // arena free again
             m.out = d.inst[buf].as<vx_instance>();
-            m.capacity = kArenaQuads;
+            m.capacity = std::min<size_t>(kArenaQuads, d.inst[buf].cap / rec);
             m.m0 = a;
             m.quad_base = h_off[a];
             m.status = d.st();
@@ -363,6 +371,29 @@ void destroy_dev(Dev &d)
     if (d.aux) cudaStreamDestroy(d.aux);
     if (d.fork) cudaEventDestroy(d.fork);
     if (d.join) cudaEventDestroy(d.join);
+}
+
+// Runs fn(device index) for every device of a multi-GPU context, one host thread per device, so that a
+// blocking step on one GPU (a D2H into pageable caller memory only returns when the copy is done) does
+// not hold back the launches of the others.  Errors keep their text: vx_last_error is thread-local.
+int for_each_device(size_t nd, const std::function<int(size_t)> &fn)
+{
+    if (nd == 1) return fn(0);
+    std::vector<int> rc(nd, VX_OK);
+    std::vector<std::string> msg(nd);
+    std::vector<std::thread> th;
+    for (size_t di = 0; di < nd; ++di)
+        th.emplace_back([&, di] {
+            rc[di] = fn(di);
+            if (rc[di] != VX_OK) msg[di] = g_err;
+        });
+    for (auto &t : th) t.join();
+    for (size_t di = 0; di < nd; ++di)
+        if (rc[di] != VX_OK) {
+            g_err = msg[di];
+            return rc[di];
+        }
+    return VX_OK;
 }
 
 // Lease of one lane for the duration of a short-list call.
@@ -477,7 +508,7 @@ int vx_create(const int *devices, int n_devices, vx_ctx **out)
     for (int id : ids)
         if (id < 0 || id >= avail) return fail(VX_ERR_BAD_ARG, "device %d out of range (have %d)", id, avail);
     vx_ctx *ctx = new vx_ctx();
-    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) ctx->devs.emplace_back();
     for (size_t i = 0; i < ids.size(); ++i) {
         const cudaError_t e = init_dev(ctx->devs[i], ids[i]);
         if (e != cudaSuccess) {
@@ -646,7 +677,7 @@ static int mesh_prepare(Dev &d, cudaStream_t s, const int32_t *d_coords, uint32_
     TIMED(d, s, VX_K_PACK, vx_launch_pack(d_blocks, n, d.occ.as<uint32_t>(), d.typ.as<uint32_t>(), d_status, s, &d.launches));
     if (d_nbr_idx) {
         CK(d.nbr.ensure((size_t)n * 16));
-        TIMED(d, s, VX_K_RESOLVE, vx_launch_remap_nbr(d_nbr_idx, d.nbr.as<int32_t>(), n, s, &d.launches));
+        TIMED(d, s, VX_K_RESOLVE, vx_launch_remap_nbr(d_nbr_idx, d.nbr.as<int32_t>(), n, d_status, s, &d.launches));
     } else {
         RET(dev_resolve(d, s, d_coords, n, 0, n, nullptr, false));
     }
@@ -672,7 +703,10 @@ int vx_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *
         CK(cudaMemsetAsync(offsets, 0, 8, s));
         return VX_OK;
     }
+    d.last_n = 0;
     RET(mesh_prepare(d, s, coords, (uint32_t)n, blocks, nbr_idx, counts, offsets, mesh_mask, status));
+    d.last_n = mesh_mask ? 0 : n;          // (a masked batch is not replayable: the mask is the caller's)
+    d.last_typ = true;
     if (instances) {
         vx_mesh_args m = emit_args(d, coords, d.typ.as<uint32_t>(), mesh_mask, counts, offsets, (uint32_t)n);
         m.out = instances;
@@ -693,6 +727,9 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
     if (n > (size_t)0x3ffffff) return fail(VX_ERR_BAD_ARG, "n too large for one call (%zu)", n);
     offsets[0] = 0;
     if (n == 0) return VX_OK;
+    if (nbr_idx)        // validated before anything is enqueued
+        for (size_t i = 0; i < n * 4; ++i)
+            if (nbr_idx[i] >= (int64_t)n) return fail(VX_ERR_BAD_ARG, "nbr_idx[%zu] = %d out of range", i, nbr_idx[i]);
     DevGuard guard(ctx, n);
     if (!guard.d) return cuda_fail(guard.err, "lane setup", __LINE__);
     Dev &d = *guard.d;
@@ -707,8 +744,6 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
     CK(cudaMemcpyAsync(d.blocks.p, blocks, n * VX_VOXELS, cudaMemcpyHostToDevice, s));
     const int32_t *d_nbr_idx = nullptr;
     if (nbr_idx) {
-        for (size_t i = 0; i < n * 4; ++i)
-            if (nbr_idx[i] >= (int64_t)n) return fail(VX_ERR_BAD_ARG, "nbr_idx[%zu] = %d out of range", i, nbr_idx[i]);
         CK(d.nbr_in.ensure(n * 16));
         CK(cudaMemcpyAsync(d.nbr_in.p, nbr_idx, n * 16, cudaMemcpyHostToDevice, s));
         d_nbr_idx = d.nbr_in.as<int32_t>();
@@ -762,7 +797,10 @@ static int gen_mesh_device_impl(vx_ctx *ctx, const int32_t *coords, size_t n, co
         return VX_OK;
     }
     const uint32_t nn = (uint32_t)n;
+    d.last_n = 0;
     RET(dev_gen_count(d, s, coords, nn, 0, nn, p, nbr_mask, counts, offsets, blocks_out));
+    d.last_n = n;
+    d.last_typ = false;
     if (instances) {
         vx_mesh_args m = emit_args(d, coords, nullptr, nullptr, counts, offsets, nn);
         m.out = static_cast<vx_instance *>(instances);
@@ -780,6 +818,26 @@ int vx_gen_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_no
 {
     return gen_mesh_device_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, status,
                                 blocks_out, stream, false);
+}
+
+int vx_emit_again_device(vx_ctx *ctx, const int32_t *coords, size_t n, uint32_t *counts, uint64_t *offsets,
+                         vx_instance *instances, size_t capacity, uint32_t *status, void *stream)
+{
+    if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
+    if (n == 0) return VX_OK;
+    if (!coords || !counts || !offsets || !instances) return fail(VX_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dev &d = ctx->devs[0];
+    if (d.last_n != n) return fail(VX_ERR_BAD_ARG, "the context's last device batch had %zu chunks, not %zu", d.last_n, n);
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = stream ? (cudaStream_t)stream : d.stream;
+    if (status) CK(cudaMemsetAsync(status, 0, 4, s));
+    vx_mesh_args m = emit_args(d, coords, d.last_typ ? d.typ.as<uint32_t>() : nullptr, nullptr, counts, offsets, (uint32_t)n);
+    m.out = instances;
+    m.capacity = capacity;
+    m.status = status;
+    TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, (uint32_t)n, s, &d.launches));
+    return VX_OK;
 }
 
 int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
@@ -908,11 +966,11 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
     std::vector<uint32_t> lo(nd), hi(nd);
     std::vector<std::vector<uint64_t>> loc(nd);     // device-local offsets
 
-    for (size_t di = 0; di < nd; ++di) {
+    RET(for_each_device(nd, [&](size_t di) -> int {
         Dev &d = ctx->devs[di];
         split_range(n, nd, di, 1, &lo[di], &hi[di]);
         const uint32_t c = hi[di] - lo[di];
-        if (c == 0) continue;
+        if (c == 0) return VX_OK;
         CK(cudaSetDevice(d.id));
         CK(d.coords.ensure(n * 12));
         CK(cudaMemcpyAsync(d.coords.p, coords, n * 12, cudaMemcpyHostToDevice, d.stream));
@@ -938,14 +996,13 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
         if (blocks_out)
             CK(cudaMemcpyAsync(blocks_out + (size_t)lo[di] * VX_VOXELS, d.blocks.p, (size_t)c * VX_VOXELS,
                                cudaMemcpyDeviceToHost, d.stream));
-    }
+        CK(cudaStreamSynchronize(d.stream));
+        return VX_OK;
+    }));
     uint64_t total = 0;
     std::vector<uint64_t> base(nd, 0);
     for (size_t di = 0; di < nd; ++di) {
         if (hi[di] == lo[di]) continue;
-        Dev &d = ctx->devs[di];
-        CK(cudaSetDevice(d.id));
-        CK(cudaStreamSynchronize(d.stream));
         base[di] = total;
         const uint32_t c = hi[di] - lo[di];
         for (uint32_t i = 0; i < c; ++i) offsets[lo[di] + i] = total + loc[di][i];
@@ -956,17 +1013,16 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
     if (!instances) return VX_OK;
     if (total > capacity)
         return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
-    for (size_t di = 0; di < nd; ++di) {
+    return for_each_device(nd, [&](size_t di) -> int {
         const uint32_t c = hi[di] - lo[di];
-        if (c == 0) continue;
+        if (c == 0) return VX_OK;
         Dev &d = ctx->devs[di];
         CK(cudaSetDevice(d.id));
         vx_mesh_args m = emit_args(d, d.coords.as<int32_t>() + 3 * (size_t)lo[di], nullptr, nullptr,
                                    d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), c);
         RET(dev_stream_instances(d, m, loc[di].data(), c, instances + base[di] * rec, packed));
-    }
-    for (Dev &d : ctx->devs) RET(sync_dev(d));
-    return VX_OK;
+        return sync_dev(d);
+    });
 }
 
 int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
@@ -1041,7 +1097,8 @@ static int frustum_host(vx_ctx *ctx, const float *planes, size_t n_frames, const
         CK(d.coords.ensure(c * 12));
         CK(cudaMemcpyAsync(d.coords.p, coords + 3 * (size_t)lo, c * 12, cudaMemcpyHostToDevice, d.stream));
         const size_t per_frame = visible ? c : cw * 4;
-        const size_t fs = std::min(n_frames, std::max<size_t>(1, kSliceBytes / per_frame));
+        // frames per launch: the staging slice, and gridDim.y = ceil(frames / 64) <= 65535
+        const size_t fs = std::min({n_frames, std::max<size_t>(1, kSliceBytes / per_frame), (size_t)65535 * 64});
         CK(d.planes.ensure(n_frames * 96));
         CK(cudaMemcpyAsync(d.planes.p, planes, n_frames * 96, cudaMemcpyHostToDevice, d.stream));
         if (visible) CK(d.vis.ensure(fs * c));

@@ -82,12 +82,100 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
     }
 }
 
+// ---------------------------------------------------------------------------
+// One plane set per launch (the reference's own call shape: Frustum::contains against the current
+// camera, chunk_builder.rs:251 / world.rs:35, for every loaded chunk).  13 bytes per test, so the launch
+// is latency-bound: there is no shared-memory staging and no CTA barrier.  A thread owns FOUR consecutive
+// chunks whose 12 coordinates arrive as three 128-bit loads (a warp reads 1536 contiguous bytes); the
+// six planes are six uniform 128-bit loads issued beside them.  Same arithmetic and the same warp-level
+// plane skipping as the general kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool aabb_visible(const float4 (&pl)[6], int32_t cx, int32_t cy, int32_t cz, bool live)
+{
+    const float x0 = (float)(int32_t)((uint32_t)cx * 32u), y0 = (float)(int32_t)((uint32_t)cy * 32u),
+                z0 = (float)(int32_t)((uint32_t)cz * 32u);
+    const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
+    const float inf = __int_as_float(0x7f800000);
+    float m0 = inf, m1 = inf, m2 = inf, m3 = inf, m4 = inf, m5 = inf, m6 = inf, m7 = inf;
+#pragma unroll
+    for (uint32_t p = 0; p < 6; ++p) {
+        const float ax0 = __fmul_rn(pl[p].x, x0), ax1 = __fmul_rn(pl[p].x, x1);
+        const float by0 = __fmul_rn(pl[p].y, y0), by1 = __fmul_rn(pl[p].y, y1);
+        const float cz0 = __fmul_rn(pl[p].z, z0), cz1 = __fmul_rn(pl[p].z, z1);
+        const float s00 = __fadd_rn(ax0, by0), s10 = __fadd_rn(ax1, by0);
+        const float s01 = __fadd_rn(ax0, by1), s11 = __fadd_rn(ax1, by1);
+        m0 = fminf(m0, __fadd_rn(__fadd_rn(s00, cz0), pl[p].w));
+        m1 = fminf(m1, __fadd_rn(__fadd_rn(s10, cz0), pl[p].w));
+        m2 = fminf(m2, __fadd_rn(__fadd_rn(s00, cz1), pl[p].w));
+        m3 = fminf(m3, __fadd_rn(__fadd_rn(s10, cz1), pl[p].w));
+        m4 = fminf(m4, __fadd_rn(__fadd_rn(s01, cz0), pl[p].w));
+        m5 = fminf(m5, __fadd_rn(__fadd_rn(s11, cz0), pl[p].w));
+        m6 = fminf(m6, __fadd_rn(__fadd_rn(s01, cz1), pl[p].w));
+        m7 = fminf(m7, __fadd_rn(__fadd_rn(s11, cz1), pl[p].w));
+        if (p == 1 || p == 3) {
+            const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+            if (!__any_sync(VX_FULL, live && !(best < 0.0f))) return false;
+        }
+    }
+    const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+    return live && !(best < 0.0f);
+}
+
+template <bool WANT_BYTES, bool WANT_BITS>
+__global__ void __launch_bounds__(kThreads)
+vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restrict__ coords, uint32_t n,
+                      uint8_t *__restrict__ visible, uint32_t *__restrict__ bits)
+{
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;     // group of four chunks
+    const uint32_t i0 = g * 4u, lane = threadIdx.x & 31u;
+    if ((g & ~31u) * 4u >= n) return;                            // whole warp past the end
+    int32_t c[12];
+    if (i0 + 4u <= n) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(coords) + (size_t)g * 3;
+        const uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < 12; ++k) c[k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
+    }
+    float4 pl[6];
+#pragma unroll
+    for (uint32_t p = 0; p < 6; ++p) pl[p] = __ldg(reinterpret_cast<const float4 *>(planes) + p);
+    uint32_t nib = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+        nib |= (aabb_visible(pl, c[3 * k], c[3 * k + 1], c[3 * k + 2], i0 + k < n) ? 1u : 0u) << k;
+    if (WANT_BYTES && i0 < n) {
+        const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;           // visible is 4-byte aligned (launcher)
+        else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+    }
+    if (WANT_BITS) {
+        // eight lanes hold one 32-chunk word
+        uint32_t v = nib << (4u * (lane & 7u));
+        v |= __shfl_xor_sync(VX_FULL, v, 1);
+        v |= __shfl_xor_sync(VX_FULL, v, 2);
+        v |= __shfl_xor_sync(VX_FULL, v, 4);
+        if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
+    }
+}
+
 }  // namespace
 
 cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
                               uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches)
 {
     if (n == 0 || n_frames == 0) return cudaSuccess;
+    if (n_frames == 1 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15u) == 0 &&
+        (!visible || (reinterpret_cast<uintptr_t>(visible) & 3u) == 0)) {
+        const uint32_t groups = (n + 3u) / 4u, g1 = (groups + kThreads - 1) / kThreads;
+        if (visible && bits) vx_frustum_one_kernel<true, true><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+        else if (visible) vx_frustum_one_kernel<true, false><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+        else vx_frustum_one_kernel<false, true><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     const dim3 grid((n + kThreads - 1) / kThreads, (n_frames + kFramesPerCta - 1) / kFramesPerCta);
     const uint32_t n_words = (n + 31) / 32;
     if (visible && bits)

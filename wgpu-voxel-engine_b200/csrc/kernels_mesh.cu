@@ -203,10 +203,19 @@ __global__ void __launch_bounds__(1024) vx_resolve_small_kernel(const vx_resolve
 }
 
 // caller-provided nbr_idx (>= 0 index, anything negative = None)
-__global__ void vx_remap_nbr_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, uint32_t n4)
+// an index >= n would make the mesher read another allocation: it becomes None and raises a status bit
+__global__ void vx_remap_nbr_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, uint32_t n4, uint32_t n,
+                                    uint32_t *status)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n4) out[t] = in[t] >= 0 ? in[t] : VX_NBR_NONE;
+    if (t >= n4) return;
+    const int32_t v = in[t];
+    if (v >= 0 && (uint32_t)v >= n) {
+        out[t] = VX_NBR_NONE;
+        if (status) atomicOr(status, VX_ST_BAD_NBR);
+    } else {
+        out[t] = v >= 0 ? v : VX_NBR_NONE;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -422,6 +431,8 @@ struct EmitSmem {
     ChunkSmem c;
     uint32_t nz_base[VX_ROWS + 1];           // first quad of each NON-EMPTY row (+ sentinel = count)
     uint16_t nz_row[VX_ROWS];                // its row index
+    uint32_t nz_coarse[32];                  // nz_base[32 * i]: the coarse probe reads these at stride 1 (the
+                                             // stride-32 gather from nz_base itself is a 32-way bank conflict)
     __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
     uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
     uint32_t warp_tot[kEmitWarps];
@@ -483,6 +494,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         }
         s.lut[i] = v;
     }
+    if (tid >= 96 && tid < 128) s.nz_coarse[tid - 96] = 0;        // entries past the last non-empty row are never used
     if (tid < 96) {
         // coordinate.rs:60-65 + chunk.rs:66,68,76 + quad.rs:42: (chunk*32 + local) as f32
         const uint32_t axis = tid >> 5, v = tid & 31u;
@@ -520,6 +532,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         for (uint32_t j = 0; j < 4; ++j) {
             if (cnt[j]) {
                 s.nz_base[base >> 20] = base & 0xfffffu;
+                if (((base >> 20) & 31u) == 0u) s.nz_coarse[base >> 25] = base & 0xfffffu;
                 s.nz_row[base >> 20] = (uint16_t)(tid * 4 + j);
                 base += cnt[j] + (1u << 20);
             }
@@ -549,7 +562,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         const uint32_t lead = (uint32_t)(G & 3ull);            // stage word i <-> global word G - lead + i
         // Row of every quad of the tile, cooperatively: idx0 = the non-empty row holding q0 (two
         // 32-way ballots over nz_base), then each later row start inside the tile sets one bit.
-        const uint32_t c_probe = s.nz_base[min(lane * 32u, nzc)];
+        const uint32_t c_probe = s.nz_coarse[lane];
         const uint32_t cblk = __popc(__ballot_sync(VX_FULL, lane * 32u < nzc && c_probe <= q0)) - 1u;
         const uint32_t f_probe = s.nz_base[min(cblk * 32u + lane, nzc)];
         const uint32_t idx0 = cblk * 32u + __popc(__ballot_sync(VX_FULL, cblk * 32u + lane < nzc && f_probe <= q0)) - 1u;
@@ -666,11 +679,11 @@ cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t
     return cudaGetLastError();
 }
 
-cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, cudaStream_t s,
+cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, uint32_t *status, cudaStream_t s,
                                 uint64_t *launches)
 {
     if (n == 0) return cudaSuccess;
-    vx_remap_nbr_kernel<<<(n * 4 + 255) / 256, 256, 0, s>>>(nbr_in, nbr_out, n * 4);
+    vx_remap_nbr_kernel<<<(n * 4 + 255) / 256, 256, 0, s>>>(nbr_in, nbr_out, n * 4, n, status);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -10,6 +10,7 @@
 // status word bits written by device code (vx_*_device `status`)
 #define VX_ST_OVERFLOW 1u
 #define VX_ST_BAD_BLOCK 2u
+#define VX_ST_BAD_NBR 4u        /* a caller-provided nbr_idx entry >= n (treated as None) */
 
 // Neighbour reference encoding used between the resolve and mesh kernels:
 //   >= 0  : index of a full chunk in the occupancy array
@@ -75,7 +76,8 @@ struct vx_resolve_args {
     uint32_t *halo_count;       // out counter
 };
 cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t *launches);
-cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, uint32_t *status, cudaStream_t s,
+                                uint64_t *launches);
 
 cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
                               uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches);

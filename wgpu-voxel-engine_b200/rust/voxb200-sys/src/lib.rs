@@ -87,6 +87,9 @@ extern "C" {
                               blocks_out: *mut u8, stream: *mut c_void) -> c_int;
     pub fn vx_frustum_cull_device(ctx: *mut vx_ctx, planes: *const f32, n_frames: usize, coords: *const i32,
                                   n: usize, visible: *mut u8, bits: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn vx_emit_again_device(ctx: *mut vx_ctx, coords: *const i32, n: usize, counts: *mut u32,
+                                offsets: *mut u64, instances: *mut vx_instance, capacity: usize,
+                                status: *mut u32, stream: *mut c_void) -> c_int;
     pub fn vx_sync(ctx: *mut vx_ctx) -> c_int;
     pub fn vx_measure_peak(ctx: *mut vx_ctx, kind: c_int, tera_ops: *mut f64) -> c_int;
     pub fn vx_set_timing(ctx: *mut vx_ctx, on: c_int) -> c_int;

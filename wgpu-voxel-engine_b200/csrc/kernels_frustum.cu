@@ -121,44 +121,64 @@ __device__ __forceinline__ bool aabb_visible(const float4 (&pl)[6], int32_t cx, 
     return live && !(best < 0.0f);
 }
 
-template <bool WANT_BYTES, bool WANT_BITS>
+// G groups of four chunks per thread (group g of round r = r * threads + thread: every round is a
+// coalesced sweep).  The launcher picks G so that the whole grid is resident at once -- one wave, all
+// loads of a thread issued up front.
+template <bool WANT_BYTES, bool WANT_BITS, int G>
 __global__ void __launch_bounds__(kThreads)
 vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restrict__ coords, uint32_t n,
                       uint8_t *__restrict__ visible, uint32_t *__restrict__ bits)
 {
-    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;     // group of four chunks
-    const uint32_t i0 = g * 4u, lane = threadIdx.x & 31u;
-    if ((g & ~31u) * 4u >= n) return;                            // whole warp past the end
-    int32_t c[12];
-    if (i0 + 4u <= n) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(coords) + (size_t)g * 3;
-        const uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
-        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-        c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
-    } else {
+    const uint32_t lane = threadIdx.x & 31u, stride = gridDim.x * kThreads;
+    const uint32_t g0 = blockIdx.x * kThreads + threadIdx.x;     // first group of four chunks
+    int32_t c[G][12];
 #pragma unroll
-        for (uint32_t k = 0; k < 12; ++k) c[k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
+    for (int r = 0; r < G; ++r) {
+        const uint32_t g = g0 + r * stride, i0 = g * 4u;
+        if (i0 + 4u <= n) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(coords) + (size_t)g * 3;
+            const uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+            c[r][0] = a.x; c[r][1] = a.y; c[r][2] = a.z; c[r][3] = a.w; c[r][4] = b.x; c[r][5] = b.y;
+            c[r][6] = b.z; c[r][7] = b.w; c[r][8] = d.x; c[r][9] = d.y; c[r][10] = d.z; c[r][11] = d.w;
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 12; ++k) c[r][k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
+        }
     }
     float4 pl[6];
 #pragma unroll
     for (uint32_t p = 0; p < 6; ++p) pl[p] = __ldg(reinterpret_cast<const float4 *>(planes) + p);
-    uint32_t nib = 0;
 #pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-        nib |= (aabb_visible(pl, c[3 * k], c[3 * k + 1], c[3 * k + 2], i0 + k < n) ? 1u : 0u) << k;
-    if (WANT_BYTES && i0 < n) {
-        const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-        if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;           // visible is 4-byte aligned (launcher)
-        else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+    for (int r = 0; r < G; ++r) {
+        const uint32_t g = g0 + r * stride, i0 = g * 4u;
+        if ((g & ~31u) * 4u >= n) break;                         // whole warp past the end (warp-uniform)
+        uint32_t nib = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+            nib |= (aabb_visible(pl, c[r][3 * k], c[r][3 * k + 1], c[r][3 * k + 2], i0 + k < n) ? 1u : 0u) << k;
+        if (WANT_BYTES && i0 < n) {
+            const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;       // visible is 4-byte aligned (launcher)
+            else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+        }
+        if (WANT_BITS) {
+            // eight lanes hold one 32-chunk word
+            uint32_t v = nib << (4u * (lane & 7u));
+            v |= __shfl_xor_sync(VX_FULL, v, 1);
+            v |= __shfl_xor_sync(VX_FULL, v, 2);
+            v |= __shfl_xor_sync(VX_FULL, v, 4);
+            if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
+        }
     }
-    if (WANT_BITS) {
-        // eight lanes hold one 32-chunk word
-        uint32_t v = nib << (4u * (lane & 7u));
-        v |= __shfl_xor_sync(VX_FULL, v, 1);
-        v |= __shfl_xor_sync(VX_FULL, v, 2);
-        v |= __shfl_xor_sync(VX_FULL, v, 4);
-        if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
-    }
+}
+
+template <int G>
+void launch_one(const float *planes, const int32_t *coords, uint32_t n, uint8_t *visible, uint32_t *bits, cudaStream_t s)
+{
+    const uint32_t groups = (n + 3u) / 4u, threads = (groups + G - 1) / G, g1 = (threads + kThreads - 1) / kThreads;
+    if (visible && bits) vx_frustum_one_kernel<true, true, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+    else if (visible) vx_frustum_one_kernel<true, false, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+    else vx_frustum_one_kernel<false, true, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
 }
 
 }  // namespace
@@ -169,10 +189,9 @@ cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int3
     if (n == 0 || n_frames == 0) return cudaSuccess;
     if (n_frames == 1 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15u) == 0 &&
         (!visible || (reinterpret_cast<uintptr_t>(visible) & 3u) == 0)) {
-        const uint32_t groups = (n + 3u) / 4u, g1 = (groups + kThreads - 1) / kThreads;
-        if (visible && bits) vx_frustum_one_kernel<true, true><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
-        else if (visible) vx_frustum_one_kernel<true, false><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
-        else vx_frustum_one_kernel<false, true><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+        // one wave if possible: 148 SMs x 4 resident CTAs x 256 threads x 4 chunks = 606 k chunks with G = 1
+        if (n <= 148u * 4u * kThreads * 4u) launch_one<1>(planes, coords, n, visible, bits, s);
+        else launch_one<2>(planes, coords, n, visible, bits, s);
         if (launches) ++*launches;
         return cudaGetLastError();
     }

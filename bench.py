@@ -689,11 +689,16 @@ def emit_json(obj) -> None:
         os.write(_REAL_STDOUT, data)
 
 
-def main():
+def redirect_stdout():
+    """fd 1 -> fd 2 for library chatter; the JSON line goes to the saved real stdout (after a possible re-exec
+    under torchrun, so that the ranks inherit the caller's stdout)."""
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+
+
+def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -707,6 +712,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        redirect_stdout()
         run_reference(args, rank, world)
         return
     if args.gpus > 1 and world == 1:
@@ -718,6 +724,7 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                                    "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    redirect_stdout()
     run_ours(args, rank, world, local_rank)
 
 

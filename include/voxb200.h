@@ -166,6 +166,30 @@ int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, cons
                               const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets,
                               uint32_t *quads, size_t capacity, uint32_t *status, void *stream);
 
+/* ---- extension: vertical neighbours and a DIRT rule -----------
+ * NOT reference behaviour: the reference never consults a chunk's -y / +y neighbours (every face on a
+ * y border is emitted, chunk.rs:205-240) and never generates DIRT (cube.rs:19, texture.rs:242).
+ *   vertical_neighbours  nbr_mask bits 4 (-y) and 5 (+y) are honoured: a present vertical neighbour hides
+ *                        the border faces it covers, exactly like the x / z rule of chunk.rs:89-108; an
+ *                        absent one leaves them emitted.  With nbr_mask == NULL a vertical neighbour is
+ *                        present iff it is in the list.
+ *   dirt_rule            a solid voxel whose +y neighbour voxel is solid is DIRT (texture layer 1 on all six
+ *                        faces, texture.rs:242), else GRASS; the voxel above y = 31 is looked up in the +y
+ *                        chunk when vertical_neighbours says it is present, else it counts as air.
+ * opts == NULL, or both fields 0, is vx_gen_mesh.  blocks_out then carries DIRT (1) as well. */
+typedef struct vx_terrain_opts {
+    uint32_t vertical_neighbours;
+    uint32_t dirt_rule;
+} vx_terrain_opts;
+int vx_gen_mesh_ex(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                   const vx_terrain_opts *opts, const uint8_t *nbr_mask,
+                   uint32_t *counts, uint64_t *offsets, vx_instance *instances, size_t capacity,
+                   uint64_t *total_out, uint8_t *blocks_out);
+int vx_gen_mesh_ex_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                          const vx_terrain_opts *opts, const uint8_t *nbr_mask,
+                          uint32_t *counts, uint64_t *offsets, vx_instance *instances, size_t capacity,
+                          uint32_t *status, uint8_t *blocks_out, void *stream);
+
 /* ---- frustum -------------------------------------------------------------
  * vx_planes_from_matrix replaces Frustum::matrix_to_planes
  * (frustum_culling.rs:47-85): m = column-major Matrix4<f32> (m[c*4+r]),

@@ -73,6 +73,12 @@ def lib():
         L.vxo_gen_mesh_batch.restype = sz
         L.vxo_gen_mesh_batch.argtypes = [i32p, sz, C.POINTER(NoiseParams), vp, C.c_int, C.c_int,
                                          vp, vp, vp, sz, vp]
+        L.vxo_gen_mesh_batch_ex.restype = sz
+        L.vxo_gen_mesh_batch_ex.argtypes = [i32p, sz, C.POINTER(NoiseParams), vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            vp, vp, vp, sz, vp]
+        L.vxo_dirt_rule.argtypes = [vp, vp]
+        L.vxo_create_mesh_ex.restype = sz
+        L.vxo_create_mesh_ex.argtypes = [i32p, vp, C.POINTER(vp), vp, sz]
         L.vxo_mesh_batch.restype = sz
         L.vxo_mesh_batch.argtypes = [i32p, sz, vp, vp, C.c_int, vp, vp, vp, sz]
         _lib = L
@@ -179,8 +185,12 @@ def frustum_cull(planes, coords) -> np.ndarray:
 
 
 def gen_mesh_batch(coords, params=None, nbr_mask=None, nthreads=None, use_simd=True,
-                   want_instances=True, want_cubes=False):
-    """Returns dict(counts, offsets, instances|None, cubes|None, total)."""
+                   want_instances=True, want_cubes=False, vertical=False, dirt_rule=False):
+    """Returns dict(counts, offsets, instances|None, cubes|None, total).
+    vertical / dirt_rule: the SURVEY 8(f4) extension (vxo_gen_mesh_batch_ex)."""
+    if vertical or dirt_rule:
+        return _gen_mesh_batch_ex(coords, params, nbr_mask, nthreads, use_simd, want_instances, want_cubes,
+                                  vertical, dirt_rule)
     p = params or default_params()
     coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
     n = coords.shape[0]
@@ -207,6 +217,37 @@ def gen_mesh_batch(coords, params=None, nbr_mask=None, nthreads=None, use_simd=T
     if total == C.c_size_t(-1).value:
         raise RuntimeError("oracle batch failed")
     return dict(counts=counts, offsets=offsets, instances=inst, cubes=cubes, total=int(total))
+
+
+def _gen_mesh_batch_ex(coords, params, nbr_mask, nthreads, use_simd, want_instances, want_cubes, vertical, dirt_rule):
+    p = params or default_params()
+    coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
+    n = coords.shape[0]
+    nthreads = nthreads or os.cpu_count() or 1
+    counts = np.zeros(n, dtype=np.uint32)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    cubes = np.empty((n, VOXELS), dtype=np.uint8) if want_cubes else None
+    mask = None if nbr_mask is None else np.ascontiguousarray(nbr_mask, dtype=np.uint8)
+
+    def call(inst, cap):
+        return lib().vxo_gen_mesh_batch_ex(_ptr(coords), n, C.byref(p), _ptr(mask), int(vertical), int(dirt_rule),
+                                           nthreads, int(use_simd), _ptr(counts), _ptr(offsets), _ptr(inst), cap,
+                                           _ptr(cubes))
+    total = call(None, 0)
+    inst = None
+    if want_instances:
+        inst = np.empty(int(total), dtype=INSTANCE_DTYPE)
+        total = call(inst, int(total))
+    if total == C.c_size_t(-1).value:
+        raise RuntimeError("oracle batch failed")
+    return dict(counts=counts, offsets=offsets, instances=inst, cubes=cubes, total=int(total))
+
+
+def dirt_rule(cubes, above=None) -> np.ndarray:
+    out = np.ascontiguousarray(cubes, dtype=np.uint8).reshape(VOXELS).copy()
+    ab = None if above is None else np.ascontiguousarray(above, dtype=np.uint8).reshape(VOXELS)
+    lib().vxo_dirt_rule(_ptr(out), _ptr(ab))
+    return out
 
 
 def mesh_batch(coords, cubes, nbr_idx, nthreads=None, want_instances=True):

@@ -355,8 +355,10 @@ static const uint32_t TEXTURE_INDEX_LIST[2][6] = {
 
 #define CIDX(x, y, z) ((size_t)(x) + 32u * (size_t)(z) + 1024u * (size_t)(y))
 
-size_t vxo_cull_unseen_triangles(const int32_t coord[3], const uint8_t *cubes,
-                                 const uint8_t *const adj[4], vxo_quad *out, size_t cap)
+/* adj[0..3] as in the reference; adj[4] (-y) / adj[5] (+y) are the EXTENSION of SURVEY 8(f4): NULL (always, for
+ * the reference's own behaviour) emits every y-border face like chunk.rs:216-222,234-240 do. */
+static size_t cull_impl(const int32_t coord[3], const uint8_t *cubes,
+                        const uint8_t *const adj[6], vxo_quad *out, size_t cap)
 {
     /* coordinate.rs:60-65 */
     const int32_t wx = (int32_t)((uint32_t)coord[0] * 32u);
@@ -405,19 +407,51 @@ size_t vxo_cull_unseen_triangles(const int32_t coord[3], const uint8_t *cubes,
                 } else if (adj[3]) {
                     if (adj[3][CIDX(x, y, 0)] == VXO_AIR) PUSH(VXO_FRONT, 3);
                 } else PUSH(VXO_FRONT, 3);
-                /* DOWN :205-222 -- tex slot 5; y border always emits */
+                /* DOWN :205-222 -- tex slot 5; y border always emits (adj[4] is NULL for the reference) */
                 if (y > 0) {
                     if (cubes[CIDX(x, y - 1, z)] == VXO_AIR) PUSH(VXO_DOWN, 5);
+                } else if (adj[4]) {
+                    if (adj[4][CIDX(x, 31, z)] == VXO_AIR) PUSH(VXO_DOWN, 5);     /* extension: same rule as x / z */
                 } else PUSH(VXO_DOWN, 5);
-                /* UP :223-240 -- tex slot 4; y border always emits */
+                /* UP :223-240 -- tex slot 4; y border always emits (adj[5] is NULL for the reference) */
                 if (y < 31) {
                     if (cubes[CIDX(x, y + 1, z)] == VXO_AIR) PUSH(VXO_UP, 4);
+                } else if (adj[5]) {
+                    if (adj[5][CIDX(x, 0, z)] == VXO_AIR) PUSH(VXO_UP, 4);        /* extension */
                 } else PUSH(VXO_UP, 4);
             }
         }
     }
 #undef PUSH
     return n;
+}
+
+size_t vxo_cull_unseen_triangles(const int32_t coord[3], const uint8_t *cubes,
+                                 const uint8_t *const adj[4], vxo_quad *out, size_t cap)
+{
+    const uint8_t *a6[6] = {adj[0], adj[1], adj[2], adj[3], NULL, NULL};   /* chunk.rs:205-240: never consulted */
+    return cull_impl(coord, cubes, a6, out, cap);
+}
+
+/* EXTENSION (no reference behaviour to restate): vertical neighbours consulted like x / z ones */
+size_t vxo_cull_unseen_triangles_ex(const int32_t coord[3], const uint8_t *cubes,
+                                    const uint8_t *const adj[6], vxo_quad *out, size_t cap)
+{
+    return cull_impl(coord, cubes, adj, out, cap);
+}
+
+/* EXTENSION: the DIRT rule -- a solid voxel whose +y neighbour voxel is solid becomes DIRT (cube.rs:19 defines the
+ * type, texture.rs:242 its textures; nothing in the reference generates it).  `above` = the +y chunk or NULL. */
+void vxo_dirt_rule(uint8_t *cubes, const uint8_t *above)
+{
+    for (int y = 0; y < 32; ++y)
+        for (int z = 0; z < 32; ++z)
+            for (int x = 0; x < 32; ++x) {
+                if (cubes[CIDX(x, y, z)] == VXO_AIR) continue;
+                const int covered = (y < 31) ? cubes[CIDX(x, y + 1, z)] != VXO_AIR
+                                             : (above && above[CIDX(x, 0, z)] != VXO_AIR);
+                cubes[CIDX(x, y, z)] = covered ? VXO_DIRT : VXO_GRASS;
+            }
 }
 
 /* ------------------------------------------------------------------------ */
@@ -474,15 +508,28 @@ void vxo_quad_to_raw(const vxo_quad *q, vxo_instance_raw *out)
     out->texture_index = q->tex;
 }
 
-size_t vxo_create_mesh(const int32_t coord[3], const uint8_t *cubes,
-                       const uint8_t *const adj[4], vxo_instance_raw *out, size_t cap)
+static size_t create_mesh_impl(const int32_t coord[3], const uint8_t *cubes,
+                               const uint8_t *const adj[6], vxo_instance_raw *out, size_t cap)
 {
     vxo_quad *faces = (vxo_quad *)malloc(sizeof(vxo_quad) * 98304);
-    size_t n = vxo_cull_unseen_triangles(coord, cubes, adj, faces, 98304);
+    size_t n = cull_impl(coord, cubes, adj, faces, 98304);
     size_t m = n < cap ? n : cap;
     for (size_t i = 0; i < m; ++i) vxo_quad_to_raw(&faces[i], &out[i]);   /* chunk.rs:255 */
     free(faces);
     return n;
+}
+
+size_t vxo_create_mesh(const int32_t coord[3], const uint8_t *cubes,
+                       const uint8_t *const adj[4], vxo_instance_raw *out, size_t cap)
+{
+    const uint8_t *a6[6] = {adj[0], adj[1], adj[2], adj[3], NULL, NULL};
+    return create_mesh_impl(coord, cubes, a6, out, cap);
+}
+
+size_t vxo_create_mesh_ex(const int32_t coord[3], const uint8_t *cubes,
+                          const uint8_t *const adj[6], vxo_instance_raw *out, size_t cap)
+{
+    return create_mesh_impl(coord, cubes, adj, out, cap);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -545,7 +592,9 @@ typedef struct {
     size_t n;
     const vxo_noise_params *p;
     const uint8_t *nbr_mask;
-    const int32_t *nbr_idx;      /* resolved [n][4] */
+    const int32_t *nbr_idx;      /* resolved [n][NB] */
+    int nb;                      /* 4 (reference) or 6 (extension: -y, +y appended) */
+    int dirt_rule;               /* extension */
     int use_simd;
     uint8_t *cubes;              /* [n][32768] */
     uint32_t *counts;
@@ -573,18 +622,27 @@ static void *batch_worker(void *arg)
             vxo_terrain_from_noise(noise, b->cubes + i * VXO_VOXELS);
         }
     }
-    pthread_barrier_wait(&b->bar);
+    int serial = pthread_barrier_wait(&b->bar);
+    if (b->dirt_rule) {
+        /* extension: types from solidity (which no thread changes), by one thread */
+        if (serial == PTHREAD_BARRIER_SERIAL_THREAD && !atomic_load(&b->failed))
+            for (size_t i = 0; i < b->n; ++i) {
+                int32_t j = (b->nb == 6) ? b->nbr_idx[6 * i + 5] : -1;
+                vxo_dirt_rule(b->cubes + i * VXO_VOXELS, j >= 0 ? b->cubes + (size_t)j * VXO_VOXELS : NULL);
+            }
+        pthread_barrier_wait(&b->bar);
+    }
     /* phase B: create_mesh (chunk.rs:48-57) */
     if (!atomic_load(&b->failed)) {
         for (;;) {
             size_t i = atomic_fetch_add(&b->next_b, 1);
             if (i >= b->n) break;
-            const uint8_t *adj[4];
-            for (int k = 0; k < 4; ++k) {
-                int32_t j = b->nbr_idx[4 * i + k];
+            const uint8_t *adj[6] = {NULL, NULL, NULL, NULL, NULL, NULL};
+            for (int k = 0; k < b->nb; ++k) {
+                int32_t j = b->nbr_idx[(size_t)b->nb * i + k];
                 adj[k] = (j >= 0) ? b->cubes + (size_t)j * VXO_VOXELS : NULL;
             }
-            size_t q = vxo_create_mesh(b->coords + 3 * i, b->cubes + i * VXO_VOXELS, adj, tmp, 98304);
+            size_t q = create_mesh_impl(b->coords + 3 * i, b->cubes + i * VXO_VOXELS, adj, tmp, 98304);
             b->counts[i] = (uint32_t)q;
             if (b->keep) {
                 vxo_instance_raw *v = (vxo_instance_raw *)malloc(sizeof(vxo_instance_raw) * (q ? q : 1));
@@ -609,12 +667,12 @@ static uint64_t coord_hash(const int32_t *c)
     return h;
 }
 
-static int32_t *resolve_neighbours(const int32_t *coords, size_t n, const uint8_t *nbr_mask)
+static int32_t *resolve_neighbours(const int32_t *coords, size_t n, const uint8_t *nbr_mask, int nb)
 {
     size_t cap = 16;
     while (cap < 2 * n + 2) cap <<= 1;
     int32_t *table = (int32_t *)malloc(sizeof(int32_t) * cap);
-    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * 4 * (n ? n : 1));
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)nb * (n ? n : 1));
     if (!table || !idx) { free(table); free(idx); return NULL; }
     for (size_t i = 0; i < cap; ++i) table[i] = -1;
     for (size_t i = 0; i < n; ++i) {
@@ -625,10 +683,12 @@ static int32_t *resolve_neighbours(const int32_t *coords, size_t n, const uint8_
             s = (s + 1) & (cap - 1);
         }
     }
-    static const int dx[4] = {-1, 1, 0, 0}, dz[4] = {0, 0, -1, 1};   /* chunk_builder.rs:134-169 */
+    static const int dx[6] = {-1, 1, 0, 0, 0, 0}, dz[6] = {0, 0, -1, 1, 0, 0};   /* chunk_builder.rs:134-169 */
+    static const int dy[6] = {0, 0, 0, 0, -1, 1};                                /* extension slots 4, 5 */
     for (size_t i = 0; i < n; ++i)
-        for (int k = 0; k < 4; ++k) {
-            int32_t q[3] = {(int32_t)((uint32_t)coords[3 * i] + (uint32_t)dx[k]), coords[3 * i + 1],
+        for (int k = 0; k < nb; ++k) {
+            int32_t q[3] = {(int32_t)((uint32_t)coords[3 * i] + (uint32_t)dx[k]),
+                            (int32_t)((uint32_t)coords[3 * i + 1] + (uint32_t)dy[k]),
                             (int32_t)((uint32_t)coords[3 * i + 2] + (uint32_t)dz[k])};
             int32_t found = -1;
             if (!nbr_mask || (nbr_mask[i] >> k) & 1) {
@@ -638,7 +698,7 @@ static int32_t *resolve_neighbours(const int32_t *coords, size_t n, const uint8_
                     s = (s + 1) & (cap - 1);
                 }
             }
-            idx[4 * i + k] = found;
+            idx[(size_t)nb * i + k] = found;
         }
     free(table);
     return idx;
@@ -686,9 +746,34 @@ size_t vxo_gen_mesh_batch(const int32_t *coords, size_t n, const vxo_noise_param
     batch_t b;
     memset(&b, 0, sizeof b);
     b.coords = coords; b.n = n; b.p = p; b.nbr_mask = nbr_mask; b.use_simd = use_simd;
-    b.counts = counts; b.do_terrain = 1; b.keep = 1;
+    b.counts = counts; b.do_terrain = 1; b.keep = 1; b.nb = 4;
     uint8_t *cubes = cubes_out ? cubes_out : (uint8_t *)malloc((size_t)VXO_VOXELS * (n ? n : 1));
-    int32_t *idx = resolve_neighbours(coords, n, nbr_mask);
+    int32_t *idx = resolve_neighbours(coords, n, nbr_mask, 4);
+    vxo_instance_raw **pc = (vxo_instance_raw **)calloc(n ? n : 1, sizeof(*pc));
+    size_t ret = (size_t)-1;
+    if (cubes && idx && pc) {
+        b.cubes = cubes; b.nbr_idx = idx; b.per_chunk = pc;
+        ret = run_batch(&b, nthreads, offsets, inst, cap);
+    }
+    if (!cubes_out) free(cubes);
+    free(idx);
+    free(pc);
+    return ret;
+}
+
+/* EXTENSION: the same work function with vertical neighbours (mask bits 4 = -y, 5 = +y) and / or
+ * the DIRT rule.  vertical = 0 and dirt_rule = 0 is vxo_gen_mesh_batch. */
+size_t vxo_gen_mesh_batch_ex(const int32_t *coords, size_t n, const vxo_noise_params *p,
+                             const uint8_t *nbr_mask, int vertical, int dirt_rule, int nthreads, int use_simd,
+                             uint32_t *counts, uint64_t *offsets,
+                             vxo_instance_raw *inst, size_t cap, uint8_t *cubes_out)
+{
+    batch_t b;
+    memset(&b, 0, sizeof b);
+    b.coords = coords; b.n = n; b.p = p; b.nbr_mask = nbr_mask; b.use_simd = use_simd;
+    b.counts = counts; b.do_terrain = 1; b.keep = 1; b.nb = vertical ? 6 : 4; b.dirt_rule = dirt_rule;
+    uint8_t *cubes = cubes_out ? cubes_out : (uint8_t *)malloc((size_t)VXO_VOXELS * (n ? n : 1));
+    int32_t *idx = resolve_neighbours(coords, n, nbr_mask, b.nb);
     vxo_instance_raw **pc = (vxo_instance_raw **)calloc(n ? n : 1, sizeof(*pc));
     size_t ret = (size_t)-1;
     if (cubes && idx && pc) {
@@ -708,7 +793,7 @@ size_t vxo_mesh_batch(const int32_t *coords, size_t n, const uint8_t *cubes,
 {
     batch_t b;
     memset(&b, 0, sizeof b);
-    b.coords = coords; b.n = n; b.counts = counts; b.do_terrain = 0; b.keep = 1;
+    b.coords = coords; b.n = n; b.counts = counts; b.do_terrain = 0; b.keep = 1; b.nb = 4;
     b.cubes = (uint8_t *)cubes; b.nbr_idx = nbr_idx;
     vxo_instance_raw **pc = (vxo_instance_raw **)calloc(n ? n : 1, sizeof(*pc));
     if (!pc) return (size_t)-1;

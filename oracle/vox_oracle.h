@@ -120,6 +120,19 @@ size_t vxo_gen_mesh_batch(const int32_t *coords, size_t n, const vxo_noise_param
                           uint32_t *counts, uint64_t *offsets,
                           vxo_instance_raw *inst, size_t cap, uint8_t *cubes_out);
 
+/* ---- EXTENSION -- not a restatement: the reference never consults vertical neighbours
+ * (chunk.rs:205-240) and never generates DIRT (cube.rs:19).  These define the extension's semantics by analogy
+ * with the reference's own x / z border rule so that the CUDA path has something to be checked against. */
+size_t vxo_cull_unseen_triangles_ex(const int32_t coord[3], const uint8_t *cubes,
+                                    const uint8_t *const adj[6] /* -x,+x,-z,+z,-y,+y */, vxo_quad *out, size_t cap);
+size_t vxo_create_mesh_ex(const int32_t coord[3], const uint8_t *cubes,
+                          const uint8_t *const adj[6], vxo_instance_raw *out, size_t cap);
+void vxo_dirt_rule(uint8_t *cubes, const uint8_t *above /* the +y chunk, or NULL */);
+size_t vxo_gen_mesh_batch_ex(const int32_t *coords, size_t n, const vxo_noise_params *p,
+                             const uint8_t *nbr_mask /* bits 0-5 */, int vertical, int dirt_rule,
+                             int nthreads, int use_simd, uint32_t *counts, uint64_t *offsets,
+                             vxo_instance_raw *inst, size_t cap, uint8_t *cubes_out);
+
 /* mesher-only variant over caller-provided block grids (config 4) */
 size_t vxo_mesh_batch(const int32_t *coords, size_t n, const uint8_t *cubes,
                       const int32_t *nbr_idx /* [n][4], -1 = None */, int nthreads,

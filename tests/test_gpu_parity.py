@@ -811,3 +811,73 @@ def test_emit_again_device(ctx, vox):
         assert a[:host.total * 17].cpu().numpy().tobytes() == host.instances.tobytes()
         with pytest.raises(vox.VoxError):
             c2.emit_again_device(d_coords.data_ptr(), n - 1, d_counts.data_ptr(), d_off.data_ptr(), b.data_ptr(), cap)
+
+
+# ---- SURVEY 8(f4) extension: vertical neighbours and the DIRT rule ------------------------------------------
+def _stack(x0, z0, nx, nz, ys):
+    return np.array([(x, y, z) for y in ys for z in range(z0, z0 + nz) for x in range(x0, x0 + nx)], np.int32)
+
+
+@pytest.mark.parametrize("vertical,dirt", [(True, False), (False, True), (True, True)])
+def test_vertical_neighbours_and_dirt_rule(ctx, oracle, vertical, dirt):
+    """vx_gen_mesh_ex: in-list vertical neighbours, masked ones, halo ones (present but not in the list), DIRT under
+    cover incl. across the chunk border -- blocks, counts and instance bytes equal the oracle's extension."""
+    coords = _stack(-1, 2, 3, 2, (-1, 0, 1))                        # 3 layers of 3 x 2 chunks
+    got = ctx.gen_mesh(coords, blocks=True, vertical=vertical, dirt_rule=dirt)
+    want = oracle.gen_mesh_batch(coords, want_cubes=True, vertical=vertical, dirt_rule=dirt)
+    assert np.array_equal(got.blocks, want["cubes"])
+    assert np.array_equal(got.counts, want["counts"])
+    assert _canon(got.instances).tobytes() == _canon(want["instances"]).tobytes()
+    if dirt:
+        assert (got.blocks == 1).any() and set(np.unique(got.instances["texture_index"]).tolist()) == {0, 1, 2}
+    if vertical:
+        ref = ctx.gen_mesh(coords)                                   # reference rule: y borders always emitted
+        assert got.total < ref.total
+    # explicit masks: random 6-bit masks; present neighbours that are not in the list become halo slabs
+    rng = np.random.default_rng(11)
+    sub = coords[[0, 4, 7, 9, 13, 17]]
+    masks = rng.integers(0, 64, size=len(sub)).astype(np.uint8)
+    masks[1] = 63
+    got2 = ctx.gen_mesh(sub, nbr_mask=masks, blocks=True, vertical=vertical, dirt_rule=dirt)
+    for i, c in enumerate(sub):
+        cx, cy, cz = (int(v) for v in c)
+        nb6 = [(cx - 1, cy, cz), (cx + 1, cy, cz), (cx, cy, cz - 1), (cx, cy, cz + 1), (cx, cy - 1, cz), (cx, cy + 1, cz)]
+        use = 6 if vertical else 4
+        adj = [oracle.generate_terrain(nc) if (k < use and (masks[i] >> k) & 1) else None for k, nc in enumerate(nb6)]
+        cubes = oracle.generate_terrain(c)
+        if dirt:
+            cubes = oracle.dirt_rule(cubes, adj[5])
+        assert np.array_equal(got2.blocks[i], cubes)
+        arr, keep = oracle._adj_array(adj[:4])
+        a6 = (oracle.C.c_void_p * 6)()
+        keep6 = []
+        for k in range(6):
+            if adj[k] is None:
+                a6[k] = None
+            else:
+                # neighbour TYPES do not matter to the mesher (only != AIR), solidity does
+                keep6.append(np.ascontiguousarray(adj[k]))
+                a6[k] = keep6[-1].ctypes.data
+        out = np.empty(98304, dtype=oracle.INSTANCE_DTYPE)
+        cc = np.ascontiguousarray(c, np.int32)
+        nq = oracle.lib().vxo_create_mesh_ex(cc.ctypes.data, np.ascontiguousarray(cubes).ctypes.data, a6, out.ctypes.data, 98304)
+        assert got2.counts[i] == nq
+        assert _canon(got2.chunk(i)).tobytes() == _canon(out[:nq]).tobytes()
+
+
+def test_terrain_opts_off_is_the_reference_path(ctx):
+    coords = _stack(0, 0, 2, 2, (0, 1))
+    a = ctx.gen_mesh(coords, blocks=True)
+    import ctypes as C
+    from voxb200._lib import TerrainOpts
+    n = len(coords)
+    counts = np.zeros(n, np.uint32)
+    offsets = np.zeros(n + 1, np.uint64)
+    inst = np.empty(a.total, a.instances.dtype)
+    blocks = np.empty((n, 32768), np.uint8)
+    total = C.c_uint64(0)
+    opts = TerrainOpts(0, 0)
+    rc = ctx._L.vx_gen_mesh_ex(ctx._h, coords.ctypes.data, n, None, C.byref(opts), None, counts.ctypes.data,
+                               offsets.ctypes.data, inst.ctypes.data, len(inst), C.addressof(total), blocks.ctypes.data)
+    assert rc == 0 and total.value == a.total
+    assert inst.tobytes() == a.instances.tobytes() and np.array_equal(blocks, a.blocks)

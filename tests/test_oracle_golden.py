@@ -213,3 +213,55 @@ def test_batch_driver_matches_single_calls(oracle):
     res0 = oracle.gen_mesh_batch(coords, nbr_mask=np.zeros(len(coords), np.uint8), nthreads=2)
     for i, c in enumerate(coords):
         assert res0["counts"][i] == len(oracle.cull_unseen_triangles(c, cubes[tuple(c)], None))
+
+
+def test_extension_vertical_neighbours_and_dirt_rule(oracle):
+    """SURVEY 8(f4) extension semantics (no reference behaviour): vertical neighbours follow the x / z border
+    rule of chunk.rs:89-108; a covered solid voxel is DIRT."""
+    solid = np.zeros(32768, dtype=np.uint8)
+    air = np.full(32768, oracle.AIR, dtype=np.uint8)
+    L = oracle.lib()
+
+    def cull6(cubes, adj6):
+        a6 = (oracle.C.c_void_p * 6)()
+        keep = []
+        for k in range(6):
+            if adj6[k] is None:
+                a6[k] = None
+            else:
+                keep.append(np.ascontiguousarray(adj6[k], dtype=np.uint8))
+                a6[k] = keep[-1].ctypes.data
+        out = np.empty(98304, dtype=oracle.INSTANCE_DTYPE)
+        c = np.zeros(3, np.int32)
+        n = L.vxo_create_mesh_ex(c.ctypes.data, cubes.ctypes.data, a6, out.ctypes.data, 98304)
+        return out[:n]
+    # all six neighbours solid: nothing is visible; none: the reference's 6 x 1024
+    assert len(cull6(solid, [solid] * 6)) == 0
+    assert len(cull6(solid, [None] * 6)) == 6 * 1024
+    # only the vertical ones solid: x / z borders stay, y borders go
+    assert len(cull6(solid, [None] * 4 + [solid, solid])) == 4 * 1024
+    # the cell consulted is the facing plane: y = 31 of the chunk below, y = 0 of the chunk above
+    below = solid.copy().reshape(32, 32, 32)
+    below[31, 9, 4] = oracle.AIR
+    inst = cull6(solid, [solid] * 4 + [below.reshape(-1), solid])
+    assert len(inst) == 1 and inst["t_matrix"][0][3].tolist() == [4.0, 0.0, 9.0, 1.0] and inst["texture_index"][0] == 1
+    # NULL vertical slots == the reference function
+    got = cull6(solid, [air, None, solid, air, None, None])
+    ref = oracle.create_mesh((0, 0, 0), solid, [air, None, solid, air])
+    assert got.tobytes() == ref.tobytes()
+    # DIRT rule: covered -> DIRT (1), uncovered -> GRASS (0); the top layer looks into the chunk above
+    col = air.copy().reshape(32, 32, 32)
+    col[0:3, 5, 5] = oracle.GRASS
+    col[31, 7, 7] = oracle.GRASS
+    d = oracle.dirt_rule(col.reshape(-1)).reshape(32, 32, 32)
+    assert d[0, 5, 5] == oracle.DIRT and d[1, 5, 5] == oracle.DIRT and d[2, 5, 5] == oracle.GRASS
+    assert d[31, 7, 7] == oracle.GRASS
+    assert oracle.dirt_rule(col.reshape(-1), above=solid).reshape(32, 32, 32)[31, 7, 7] == oracle.DIRT
+    assert (oracle.dirt_rule(col.reshape(-1)) == oracle.AIR).sum() == (col == oracle.AIR).sum()
+    # batch driver: 2 stacked chunks, vertical on/off
+    coords = np.array([(0, 0, 0), (0, 1, 0)], np.int32)
+    off = oracle.gen_mesh_batch(coords)
+    on = oracle.gen_mesh_batch(coords, vertical=True, dirt_rule=True, want_cubes=True)
+    assert on["total"] < off["total"] and (on["cubes"] == oracle.DIRT).any()
+    plain = oracle.gen_mesh_batch(coords, vertical=False, dirt_rule=False)
+    assert plain["instances"].tobytes() == off["instances"].tobytes()

@@ -170,13 +170,42 @@ def main():
                 for j in range(launches):
                     ctx.frustum_cull_device(d_pl.data_ptr() + j * F * 96, F, d_c5.data_ptr(), n5, visible_ptr=vp,
                                             bits_ptr=bp, stream=stream)
+            out_b = (n5 * F if mode == "bytes" else ((n5 + 31) // 32) * 4 * F)
             run5()
             ms = timed(run5)
+            # the loop above is bound by the host's launch path for small F (ctypes call + lock + launch ~ 10 us);
+            # device time per launch: CUDA events around every launch (vx_set_timing) and a CUDA-graph replay
+            ctx.set_timing(True)
+            run5()
+            torch.cuda.synchronize()
+            kt5 = ctx.get_timing()
+            ctx.set_timing(False)
+            dev_ms = kt5["frustum"][0] / max(kt5["frustum"][1], 1)
+            graph_ms = None
+            try:
+                g = torch.cuda.CUDAGraph()
+                ts5 = torch.cuda.Stream(device=dev)
+                with torch.cuda.graph(g, stream=ts5):
+                    for j in range(launches):
+                        ctx.frustum_cull_device(d_pl.data_ptr() + j * F * 96, F, d_c5.data_ptr(), n5, visible_ptr=vp,
+                                                bits_ptr=bp, stream=ts5.cuda_stream)
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                graph_ms = e0.elapsed_time(e1) / 5 / launches
+            except Exception as e:                       # pragma: no cover
+                graph_ms = repr(e)[:80]
             tests = n5 * F * launches
             vis = int(torch.count_nonzero(d_vis[:n5]).item()) if mode == "bytes" else None
-            out_b = (n5 * F if mode == "bytes" else ((n5 + 31) // 32) * 4 * F)
             print(json.dumps({"config": "5: frustum, %d AABBs x %d frames per launch, %s out" % (n5, F, mode),
                               "launches": launches, "ms_per_launch": ms / launches,
+                              "device_ms_per_launch_events": dev_ms, "ms_per_launch_in_cuda_graph": graph_ms,
+                              "GBps_algorithmic_device": (12 * n5 + out_b) / (dev_ms * 1e-3) / 1e9,
                               "tests_per_s": tests / (ms * 1e-3), "visible_frame0": vis,
                               "GBps_algorithmic": (12 * n5 + out_b) / (ms / launches * 1e-3) / 1e9}))
 

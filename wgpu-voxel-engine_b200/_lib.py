@@ -32,6 +32,11 @@ class NoiseParams(C.Structure):
                 ("lacunarity", C.c_float), ("octaves", C.c_int32), ("simplex_scale", C.c_float)]
 
 
+class TerrainOpts(C.Structure):
+    """vx_terrain_opts (extension)"""
+    _fields_ = [("vertical_neighbours", C.c_uint32), ("dirt_rule", C.c_uint32)]
+
+
 def build(force: bool = False) -> str:
     """Compile libvoxb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
@@ -63,6 +68,9 @@ SIGNATURES = {
     "vx_fill": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp]),
     "vx_mesh": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vx_gen_mesh": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "vx_gen_mesh_ex": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), C.POINTER(TerrainOpts), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "vx_gen_mesh_ex_device": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), C.POINTER(TerrainOpts), _vp, _vp, _vp, _vp, _sz,
+                                   _vp, _vp, _vp]),
     "vx_gen_mesh_packed": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp]),
     "vx_gen_mesh_packed_device": (_i, [_vp, _vp, _sz, C.POINTER(NoiseParams), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vx_planes_from_matrix": (_i, [_vp, _vp]),

@@ -10,7 +10,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import NoiseParams, VoxError, check
+from ._lib import NoiseParams, TerrainOpts, VoxError, check
 
 VOXELS = 32768
 ROWS = 1024
@@ -167,13 +167,20 @@ class Context:
 
     # ---- fused: the worker closure chunk_builder.rs:80-84 ---------------------
     def gen_mesh(self, coords, params: Optional[NoiseParams] = None, nbr_mask=None, instances=True,
-                 blocks=False, capacity: Optional[int] = None, out: Optional[np.ndarray] = None) -> MeshBatch:
+                 blocks=False, capacity: Optional[int] = None, out: Optional[np.ndarray] = None,
+                 vertical: bool = False, dirt_rule: bool = False) -> MeshBatch:
+        """vertical / dirt_rule: the vx_gen_mesh_ex extension (mask bits 4, 5 = -y, +y; DIRT under cover)."""
         coords = _coords(coords)
         n = coords.shape[0]
         nm = None if nbr_mask is None else np.ascontiguousarray(nbr_mask, dtype=np.uint8).reshape(n)
         b = np.empty((n, VOXELS), np.uint8) if blocks else None
+        opts = TerrainOpts(int(vertical), int(dirt_rule)) if (vertical or dirt_rule) else None
 
         def call(inst, cap, counts, offsets, total):
+            if opts is not None:
+                return self._L.vx_gen_mesh_ex(self._h, _ptr(coords), n, C.byref(params) if params else None,
+                                              C.byref(opts), _ptr(nm), _ptr(counts), _ptr(offsets), _ptr(inst), cap,
+                                              C.addressof(total), _ptr(b))
             return self._L.vx_gen_mesh(self._h, _ptr(coords), n, C.byref(params) if params else None, _ptr(nm),
                                        _ptr(counts), _ptr(offsets), _ptr(inst), cap, C.addressof(total), _ptr(b))
         res = self._run_mesh(call, n, instances, capacity, out)

@@ -92,13 +92,15 @@ struct Dev {
     cudaStream_t stream = nullptr, copy = nullptr, aux = nullptr;
     cudaEvent_t emit_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;   // aux stream: neighbour resolve + halo fill beside the main fill
-    DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_in, counts, offsets, small, blocks, noise,
+    DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_y, nbr_in, counts, offsets, small, blocks, noise,
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
     uint64_t launches = 0;
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
+    bool ex_vertical = false;      // extension state of the current batch (vx_terrain_opts): nbr_y is valid
+    int ex_dirt = 0;               // ... and the DIRT rule applies
     // optional per-kernel-class CUDA-event timing (vx_set_timing)
     std::atomic<bool> timing{false};       // read by lane callers without the context lock
     struct Stamp { cudaEvent_t a, b; int kind; };
@@ -181,15 +183,17 @@ uint32_t table_size_for(size_t n)
 
 // resolve neighbours of chunks [lo, hi) of the list into d.nbr
 int dev_resolve(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_all, uint32_t lo, uint32_t hi,
-                const uint8_t *d_mask_all, bool allow_halo)
+                const uint8_t *d_mask_all, bool allow_halo, bool vertical = false)
 {
     const uint32_t n = hi - lo;
+    const size_t slots = vertical ? 6 : 4;          // neighbour slots (halo slabs at most) per chunk
     CK(d.nbr.ensure((size_t)n * 16));
+    if (vertical) CK(d.nbr_y.ensure((size_t)n * 8));
     const uint32_t ts = table_size_for(n_all);
     CK(d.table.ensure((size_t)ts * 4));
     if (allow_halo) {
-        CK(d.halo_items.ensure((size_t)n * 4 * sizeof(vx_halo_item)));
-        CK(d.halo.ensure((size_t)n * 4 * 32 * 4));
+        CK(d.halo_items.ensure((size_t)n * slots * sizeof(vx_halo_item)));
+        CK(d.halo.ensure((size_t)n * slots * 32 * 4));
     }
     vx_resolve_args r{};
     r.coords = d_coords_all;
@@ -200,6 +204,7 @@ int dev_resolve(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_
     r.table = d.table.as<int32_t>();
     r.table_size = ts;
     r.nbr = d.nbr.as<int32_t>();
+    r.nbr_y = vertical ? d.nbr_y.as<int32_t>() : nullptr;
     r.halo_items = allow_halo ? d.halo_items.as<vx_halo_item>() : nullptr;
     r.halo_count = d.halo_count();
     TIMED(d, s, VX_K_RESOLVE, vx_launch_resolve(r, s, &d.launches));
@@ -209,9 +214,12 @@ int dev_resolve(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_
 // noise fill of chunks [lo, hi) + their halo slabs, then count + scan
 int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t n_all, uint32_t lo, uint32_t hi,
                   const vx_noise_params &p, const uint8_t *d_mask_all, uint32_t *d_counts, uint64_t *d_offsets,
-                  uint8_t *d_blocks)
+                  uint8_t *d_blocks, const vx_terrain_opts *opts = nullptr)
 {
     const uint32_t n = hi - lo;
+    d.ex_vertical = opts && opts->vertical_neighbours;
+    d.ex_dirt = (opts && opts->dirt_rule) ? 1 : 0;
+    const bool ex = d.ex_vertical || d.ex_dirt;
     if (n == 0) return VX_OK;
     CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
     const bool may_halo = d_mask_all != nullptr || lo != 0 || hi != n_all;
@@ -219,12 +227,12 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     // auxiliary stream beside the (400 us) main fill and join before the count kernel.
     CK(cudaEventRecord(d.fork, s));
     CK(cudaStreamWaitEvent(d.aux, d.fork, 0));
-    RET(dev_resolve(d, d.aux, d_coords_all, n_all, lo, hi, d_mask_all, may_halo));
+    RET(dev_resolve(d, d.aux, d_coords_all, n_all, lo, hi, d_mask_all, may_halo, d.ex_vertical));
     if (may_halo) {
         vx_fill_args h{};
         h.halo_items = d.halo_items.as<vx_halo_item>();
         h.halo_count = d.halo_count();
-        h.max_units = n * 4u;
+        h.max_units = n * (d.ex_vertical ? 6u : 4u);
         h.p = p;
         h.occ = d.halo.as<uint32_t>();
         TIMED(d, d.aux, VX_K_HALO, vx_launch_fill(h, true, d.aux, &d.launches));
@@ -236,7 +244,7 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     f.max_units = n * 32u;
     f.p = p;
     f.occ = d.occ.as<uint32_t>();
-    f.blocks = d_blocks;
+    f.blocks = ex ? nullptr : d_blocks;          // with the extension the types depend on the neighbours: written below
     TIMED(d, s, VX_K_FILL, vx_launch_fill(f, false, s, &d.launches));
     CK(cudaStreamWaitEvent(s, d.join, 0));
     vx_mesh_args m{};
@@ -245,6 +253,10 @@ int dev_gen_count(Dev &d, cudaStream_t s, const int32_t *d_coords_all, uint32_t 
     m.halo = d.halo.as<uint32_t>();
     m.coords = d_coords_all + 3 * (size_t)lo;
     m.nbr = d.nbr.as<int32_t>();
+    m.nbr_y = d.ex_vertical ? d.nbr_y.as<int32_t>() : nullptr;
+    m.dirt_rule = d.ex_dirt;
+    m.n = n;
+    if (ex && d_blocks) TIMED(d, s, VX_K_PACK, vx_launch_blocks_ex(m, d_blocks, s, &d.launches));
     m.counts = d_counts;
     m.offsets = d_offsets;
     m.n = n;
@@ -262,6 +274,8 @@ vx_mesh_args emit_args(const Dev &d, const int32_t *d_coords, const uint32_t *ty
     m.halo = d.halo.as<uint32_t>();
     m.coords = d_coords;
     m.nbr = d.nbr.as<int32_t>();
+    m.nbr_y = (!typ && d.ex_vertical) ? d.nbr_y.as<int32_t>() : nullptr;
+    m.dirt_rule = typ ? 0 : d.ex_dirt;
     m.mesh_mask = mesh_mask;
     m.counts = d_counts;
     m.offsets = d_offsets;
@@ -351,7 +365,7 @@ void destroy_dev(Dev &d)
 {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&d.coords, &d.mask8, &d.occ, &d.typ, &d.halo, &d.halo_items, &d.table, &d.nbr, &d.nbr_in,
+    for (DevBuf *b : {&d.coords, &d.mask8, &d.occ, &d.typ, &d.halo, &d.halo_items, &d.table, &d.nbr, &d.nbr_y, &d.nbr_in,
                       &d.counts, &d.offsets, &d.small, &d.blocks, &d.noise, &d.inst[0], &d.inst[1], &d.planes,
                       &d.vis, &d.bits, &d.mesh_mask})
         b->release();
@@ -672,6 +686,8 @@ static int mesh_prepare(Dev &d, cudaStream_t s, const int32_t *d_coords, uint32_
                         const int32_t *d_nbr_idx, uint32_t *d_counts, uint64_t *d_offsets,
                         const uint8_t *d_mesh_mask, uint32_t *d_status)
 {
+    d.ex_vertical = false;
+    d.ex_dirt = 0;
     CK(d.occ.ensure((size_t)n * VX_ROWS * 4));
     CK(d.typ.ensure((size_t)n * VX_ROWS * 4));
     TIMED(d, s, VX_K_PACK, vx_launch_pack(d_blocks, n, d.occ.as<uint32_t>(), d.typ.as<uint32_t>(), d_status, s, &d.launches));
@@ -780,7 +796,8 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
 // ---------------------------------------------------------------------------
 static int gen_mesh_device_impl(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
                                 const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, void *instances,
-                                size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream, bool packed)
+                                size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream, bool packed,
+                                const vx_terrain_opts *opts = nullptr)
 {
     if (!ctx) return fail(VX_ERR_BAD_ARG, "ctx is NULL");
     if (!offsets || (n && (!coords || !counts))) return fail(VX_ERR_BAD_ARG, "NULL argument");
@@ -798,7 +815,7 @@ static int gen_mesh_device_impl(vx_ctx *ctx, const int32_t *coords, size_t n, co
     }
     const uint32_t nn = (uint32_t)n;
     d.last_n = 0;
-    RET(dev_gen_count(d, s, coords, nn, 0, nn, p, nbr_mask, counts, offsets, blocks_out));
+    RET(dev_gen_count(d, s, coords, nn, 0, nn, p, nbr_mask, counts, offsets, blocks_out, opts));
     d.last_n = n;
     d.last_typ = false;
     if (instances) {
@@ -840,6 +857,14 @@ int vx_emit_again_device(vx_ctx *ctx, const int32_t *coords, size_t n, uint32_t 
     return VX_OK;
 }
 
+int vx_gen_mesh_ex_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                          const vx_terrain_opts *opts, const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets,
+                          vx_instance *instances, size_t capacity, uint32_t *status, uint8_t *blocks_out, void *stream)
+{
+    return gen_mesh_device_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, status,
+                                blocks_out, stream, false, opts);
+}
+
 int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
                               const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, uint32_t *quads,
                               size_t capacity, uint32_t *status, void *stream)
@@ -859,7 +884,8 @@ int vx_gen_mesh_packed_device(vx_ctx *ctx, const int32_t *coords, size_t n, cons
 // ---------------------------------------------------------------------------
 static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_noise_params &p,
                           const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, unsigned char *instances,
-                          size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
+                          size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed,
+                          const vx_terrain_opts *opts)
 {
     const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
     const uint32_t nn = (uint32_t)n;
@@ -883,7 +909,7 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
         d_blocks = d.blocks.as<uint8_t>();
     }
     CK(cudaMemsetAsync(d.st(), 0, 4, s));
-    RET(dev_gen_count(d, s, d.coords.as<int32_t>(), nn, 0, nn, p, d_mask, d_cnt, d_off, d_blocks));
+    RET(dev_gen_count(d, s, d.coords.as<int32_t>(), nn, 0, nn, p, d_mask, d_cnt, d_off, d_blocks, opts));
     // where the instances go: straight into a pinned caller buffer, else the arena
     void *dev_out = nullptr;
     size_t dev_cap = 0;
@@ -938,7 +964,8 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
 
 static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
                               const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets, void *instances_v,
-                              size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed)
+                              size_t capacity, uint64_t *total_out, uint8_t *blocks_out, bool packed,
+                              const vx_terrain_opts *opts = nullptr)
 {
     unsigned char *instances = static_cast<unsigned char *>(instances_v);
     const size_t rec = packed ? sizeof(uint32_t) : sizeof(vx_instance);
@@ -955,13 +982,13 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
         LaneLease lease(ctx);
         if (!lease.d) return cuda_fail(lease.err, "lane setup", __LINE__);
         return gen_mesh_short(*lease.d, coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out,
-                              blocks_out, packed);
+                              blocks_out, packed, opts);
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t nd = ctx->devs.size();
     if (n <= kShortList)
         return gen_mesh_short(ctx->devs[0], coords, n, p, nbr_mask, counts, offsets, instances, capacity, total_out,
-                              blocks_out, packed);
+                              blocks_out, packed, opts);
     const uint32_t nn = (uint32_t)n;
     std::vector<uint32_t> lo(nd), hi(nd);
     std::vector<std::vector<uint64_t>> loc(nd);     // device-local offsets
@@ -989,7 +1016,7 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
         }
         CK(cudaMemsetAsync(d.st(), 0, 4, d.stream));
         RET(dev_gen_count(d, d.stream, d.coords.as<int32_t>(), nn, lo[di], hi[di], p, d_mask,
-                          d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), d_blocks));
+                          d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), d_blocks, opts));
         loc[di].resize((size_t)c + 1);
         CK(cudaMemcpyAsync(counts + lo[di], d.counts.p, (size_t)c * 4, cudaMemcpyDeviceToHost, d.stream));
         CK(cudaMemcpyAsync(loc[di].data(), d.offsets.p, ((size_t)c + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
@@ -1031,6 +1058,14 @@ int vx_gen_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_par
 {
     return gen_mesh_host_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, total_out,
                               blocks_out, false);
+}
+
+int vx_gen_mesh_ex(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,
+                   const vx_terrain_opts *opts, const uint8_t *nbr_mask, uint32_t *counts, uint64_t *offsets,
+                   vx_instance *instances, size_t capacity, uint64_t *total_out, uint8_t *blocks_out)
+{
+    return gen_mesh_host_impl(ctx, coords, n, params, nbr_mask, counts, offsets, instances, capacity, total_out,
+                              blocks_out, false, opts);
 }
 
 int vx_gen_mesh_packed(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params *params,

@@ -41,12 +41,14 @@ vx_fill_kernel(const vx_fill_args a)
 
     int32_t cx, cy, cz;
     uint32_t item, fixed_axis_is_x = 0, fixed_val;
+    bool y_plane = false;
     if (HALO) {
         const vx_halo_item it = a.halo_items[unit];
         cx = it.cx; cy = it.cy; cz = it.cz;
         item = unit;
         fixed_axis_is_x = (it.kind < 2);
-        fixed_val = (it.kind == 0 || it.kind == 2) ? 31u : 0u;
+        fixed_val = (it.kind == 0 || it.kind == 2 || it.kind == 4) ? 31u : 0u;
+        y_plane = it.kind >= 4;
     } else {
         item = unit >> 5;
         fixed_val = unit & 31u;                    // z
@@ -59,6 +61,30 @@ vx_fill_kernel(const vx_fill_args a)
     const float ox = (float)(int32_t)((uint32_t)cx * 32u);
     const float oy = (float)(int32_t)((uint32_t)cz * 32u);
     const float oz = (float)(int32_t)((uint32_t)cy * 32u);
+    if (HALO && y_plane) {
+        // extension (vertical neighbours): the y = fixed_val plane, word z, bit x.  lane = x, the four warps of
+        // the slab take 8 z rows each; same coordinate construction and operation order as everywhere else.
+        const int oct_ = (OCT > 0) ? OCT : a.p.octaves;
+        const float fq = a.p.freq, lc = a.p.lacunarity, gn = a.p.gain, sc = a.p.simplex_scale;
+        const float x0 = __fmul_rn(__fadd_rn(ox, (float)lane), fq);
+        const float z0 = __fmul_rn(__fadd_rn(oz, (float)fixed_val), fq);
+        uint32_t word_of_lane = 0;
+        for (uint32_t zz = yq * 8u; zz < yq * 8u + 8u; ++zz) {
+            float x = x0, yy = __fmul_rn(__fadd_rn(oy, (float)zz), fq), z = z0, amp = 1.0f;
+            float r = __fmul_rn(vxn_simplex3(x, yy, z, __fadd_rn(x, yy), (uint32_t)a.p.seed), sc);
+            for (int o = 1; o < oct_; ++o) {
+                x = __fmul_rn(x, lc);
+                yy = __fmul_rn(yy, lc);
+                z = __fmul_rn(z, lc);
+                amp = __fmul_rn(amp, gn);
+                r = __fadd_rn(__fmul_rn(__fmul_rn(vxn_simplex3(x, yy, z, __fadd_rn(x, yy), (uint32_t)a.p.seed), sc), amp), r);
+            }
+            const uint32_t word = __ballot_sync(VX_FULL, r < 0.0f);
+            if (lane == zz) word_of_lane = word;
+        }
+        if ((lane >> 3) == yq) a.occ[(size_t)item * 32u + lane] = word_of_lane;
+        return;
+    }
     const uint32_t vx_ = fixed_axis_is_x ? fixed_val : lane;
     const uint32_t vz_ = fixed_axis_is_x ? lane : fixed_val;
     const float sx = __fadd_rn(ox, (float)vx_);

@@ -99,15 +99,16 @@ __global__ void vx_ht_insert_kernel(const int32_t *__restrict__ coords, uint32_t
 __global__ void vx_resolve_kernel(const vx_resolve_args a)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (a.hi - a.lo) * 4u) return;
-    const uint32_t i = a.lo + (t >> 2), k = t & 3u;
+    const uint32_t K = a.nbr_y ? 6u : 4u;                    // neighbour slots per chunk
+    if (t >= (a.hi - a.lo) * K) return;
+    const uint32_t li = t / K, i = a.lo + li, k = t - li * K;
     int32_t ref = VX_NBR_NONE;
     bool present = false;
     const bool wanted = a.nbr_mask ? ((a.nbr_mask[i] >> k) & 1u) : true;
     if (wanted) {
-        // chunk_builder.rs:134-169: k = 0:-x 1:+x 2:-z 3:+z
+        // chunk_builder.rs:134-169: k = 0:-x 1:+x 2:-z 3:+z   (extension: 4:-y 5:+y)
         const int32_t x = (int32_t)((uint32_t)a.coords[3 * i] + (k == 0 ? 0xffffffffu : (k == 1 ? 1u : 0u)));
-        const int32_t y = a.coords[3 * i + 1];
+        const int32_t y = (int32_t)((uint32_t)a.coords[3 * i + 1] + (k == 4 ? 0xffffffffu : (k == 5 ? 1u : 0u)));
         const int32_t z = (int32_t)((uint32_t)a.coords[3 * i + 2] + (k == 2 ? 0xffffffffu : (k == 3 ? 1u : 0u)));
         const uint32_t mask = a.table_size - 1u;
         uint32_t s = coord_hash(x, y, z) & mask;
@@ -132,7 +133,8 @@ __global__ void vx_resolve_kernel(const vx_resolve_args a)
             ref = vx_halo_ref((int)slot);
         }
     }
-    a.nbr[t] = ref;
+    if (k < 4u) a.nbr[4u * li + k] = ref;
+    else a.nbr_y[2u * li + (k - 4u)] = ref;
 }
 
 // Small lists (<= kSmallResolve chunks): one CTA builds the hash table in shared
@@ -177,13 +179,14 @@ __global__ void __launch_bounds__(1024) vx_resolve_small_kernel(const vx_resolve
         }
     }
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < (a.hi - a.lo) * 4u; t += blockDim.x) {
-        const uint32_t i = a.lo + (t >> 2), k = t & 3u;
+    const uint32_t K = a.nbr_y ? 6u : 4u;
+    for (uint32_t t = threadIdx.x; t < (a.hi - a.lo) * K; t += blockDim.x) {
+        const uint32_t li = t / K, i = a.lo + li, k = t - li * K;
         int32_t ref = VX_NBR_NONE;
         const bool wanted = a.nbr_mask ? ((a.nbr_mask[i] >> k) & 1u) : true;
         if (wanted) {
             const int32_t x = (int32_t)((uint32_t)co[3 * i] + (k == 0 ? 0xffffffffu : (k == 1 ? 1u : 0u)));
-            const int32_t y = co[3 * i + 1];
+            const int32_t y = (int32_t)((uint32_t)co[3 * i + 1] + (k == 4 ? 0xffffffffu : (k == 5 ? 1u : 0u)));
             const int32_t z = (int32_t)((uint32_t)co[3 * i + 2] + (k == 2 ? 0xffffffffu : (k == 3 ? 1u : 0u)));
             const int32_t j = lookup_in(table, mask, co, x, y, z);
             bool present = a.nbr_mask != nullptr || j >= 0;
@@ -196,7 +199,8 @@ __global__ void __launch_bounds__(1024) vx_resolve_small_kernel(const vx_resolve
                 ref = vx_halo_ref((int)slot);
             }
         }
-        a.nbr[t] = ref;
+        if (k < 4u) a.nbr[4u * li + k] = ref;
+        else a.nbr_y[2u * li + (k - 4u)] = ref;
     }
     __syncthreads();
     if (threadIdx.x == 0 && a.halo_count) *a.halo_count = halo_n;
@@ -241,9 +245,17 @@ __device__ __forceinline__ void stage_chunk(ChunkSmem &s, const vx_mesh_args &a,
     const int32_t nb0 = a.nbr[4 * m + 0], nb1 = a.nbr[4 * m + 1];
     const int32_t nb2 = a.nbr[4 * m + 2], nb3 = a.nbr[4 * m + 3];
     const uint32_t *own = a.occ + (size_t)m * VX_ROWS;
+    // y borders: zero rows = the reference's "always emit" (chunk.rs:216-222,234-240).  Extension: a present
+    // vertical neighbour supplies its facing plane (rows (31, z) of the chunk below, rows (0, z) of the one above).
+    const int32_t nby0 = a.nbr_y ? a.nbr_y[2 * m + 0] : VX_NBR_NONE, nby1 = a.nbr_y ? a.nbr_y[2 * m + 1] : VX_NBR_NONE;
     for (uint32_t r = tid; r < 32; r += THREADS) {
-        s.occ[r] = 0;
-        s.occ[32 + VX_ROWS + r] = 0;
+        uint32_t below = 0, above = 0;
+        if (nby0 >= 0) below = __ldg(a.occ + (size_t)nby0 * VX_ROWS + 31u * 32u + r);
+        else if (nby0 <= -2) below = __ldg(a.halo + (size_t)vx_halo_slot(nby0) * 32 + r);
+        if (nby1 >= 0) above = __ldg(a.occ + (size_t)nby1 * VX_ROWS + r);
+        else if (nby1 <= -2) above = __ldg(a.halo + (size_t)vx_halo_slot(nby1) * 32 + r);
+        s.occ[r] = below;
+        s.occ[32 + VX_ROWS + r] = above;
     }
     for (uint32_t r = tid; r < VX_ROWS; r += THREADS) s.occ[32 + r] = __ldg(own + r);
     if (tid < 32) {
@@ -383,6 +395,36 @@ vx_mesh_count_kernel(const vx_mesh_args a)
         a.counts[m] = tot;
     }
     finish_with_scan(a);
+}
+
+// ---------------------------------------------------------------------------
+// extension: CubeType bytes of a batch from its occupancy planes, with the DIRT rule (a solid voxel whose +y
+// neighbour voxel is solid is DIRT; the +y chunk's bottom plane comes through nbr_y like the mesher's)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMeshThreads)
+vx_blocks_ex_kernel(const vx_mesh_args a, uint8_t *__restrict__ blocks)
+{
+    __shared__ ChunkSmem s;
+    const uint32_t m = blockIdx.x;
+    stage_chunk<kMeshThreads>(s, a, m);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t r = threadIdx.x + j * kMeshThreads;      // row y*32 + z
+        const uint32_t o = s.occ[32 + r], d = a.dirt_rule ? (o & s.occ[32 + r + 32]) : 0u;
+        uint4 *dst = reinterpret_cast<uint4 *>(blocks + (size_t)m * VX_VOXELS + (size_t)r * 32u);
+#pragma unroll
+        for (uint32_t h = 0; h < 2u; ++h) {
+            uint32_t w[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4u; ++q) {
+                const uint32_t sh = 16u * h + 4u * q;
+                const uint32_t air = ((~o >> sh) & 15u) * 0x00204081u & 0x01010101u;       // byte k = !occ bit
+                const uint32_t drt = ((d >> sh) & 15u) * 0x00204081u & 0x01010101u;
+                w[q] = (air << 1) | drt;                         // AIR = 2, DIRT = 1, GRASS = 0 (cube.rs:16-21)
+            }
+            dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -596,7 +638,9 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
                 if (bit && seen == k) face = g;
                 seen += bit;
             }
-            const uint32_t type = typ_rows ? ((__ldg(typ_rows + r) >> x) & 1u) : 0u;
+            // block type: the caller's DIRT plane, or (extension) DIRT where the voxel above is solid
+            const uint32_t type = typ_rows ? ((__ldg(typ_rows + r) >> x) & 1u)
+                                           : (a.dirt_rule ? ((s.c.occ[32 + r + 32] >> x) & 1u) : 0u);
             if (PACKED) {
                 // 128 B per warp, coalesced
                 out32[(a.offsets[m] - a.quad_base) + q] = (r << 5) | x | (face << 15) | (type << 18);
@@ -674,7 +718,7 @@ cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t
         if (e != cudaSuccess) return e;
     }
     vx_ht_insert_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a.coords, a.n, a.table, a.table_size - 1);
-    vx_resolve_kernel<<<((a.hi - a.lo) * 4 + 255) / 256, 256, 0, s>>>(a);
+    vx_resolve_kernel<<<((a.hi - a.lo) * (a.nbr_y ? 6 : 4) + 255) / 256, 256, 0, s>>>(a);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
@@ -684,6 +728,14 @@ cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_
 {
     if (n == 0) return cudaSuccess;
     vx_remap_nbr_kernel<<<(n * 4 + 255) / 256, 256, 0, s>>>(nbr_in, nbr_out, n * 4, n, status);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, uint64_t *launches)
+{
+    if (a.n == 0) return cudaSuccess;
+    vx_blocks_ex_kernel<<<a.n, kMeshThreads, 0, s>>>(a, blocks);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -22,7 +22,8 @@ __host__ __device__ inline int vx_halo_slot(int ref) { return -ref - 2; }
 
 struct vx_halo_item {      // one 32x32 border slab of a chunk that is not in the batch
     int32_t cx, cy, cz;
-    int32_t kind;          // 0: x = 31 slab (serves a -x lookup), 1: x = 0, 2: z = 31, 3: z = 0
+    int32_t kind;          // 0: x = 31 slab (serves a -x lookup), 1: x = 0, 2: z = 31, 3: z = 0;
+                           // extension (vertical neighbours): 4: y = 31 plane (serves a -y lookup), 5: y = 0
 };
 
 // ---- launchers implemented in the kernel translation units ----------------
@@ -47,6 +48,9 @@ struct vx_mesh_args {
     const uint32_t *halo;       // [slots][32]
     const int32_t *coords;      // [n][3]
     const int32_t *nbr;         // [n][4] encoded neighbour refs
+    const int32_t *nbr_y;       // extension: [n][2] refs of the -y / +y neighbours, nullptr = reference behaviour
+                                // (y-border faces always emitted, chunk.rs:216-222,234-240)
+    int dirt_rule;              // extension: a solid voxel with a solid voxel above it is DIRT (typ == nullptr only)
     const uint8_t *mesh_mask;   // [n] or nullptr
     uint32_t *counts;           // [n]
     uint64_t *offsets;          // [n+1]
@@ -61,6 +65,8 @@ struct vx_mesh_args {
 };
 cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t *launches);
 cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches);
+// extension: CubeType bytes from the occupancy planes (+ the DIRT rule); needs the mesh args' nbr_y / halo
+cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, uint64_t *launches);
 cudaError_t vx_launch_pack(const uint8_t *blocks, uint32_t n, uint32_t *occ, uint32_t *typ,
                            uint32_t *status, cudaStream_t s, uint64_t *launches);
 
@@ -72,6 +78,7 @@ struct vx_resolve_args {
     int32_t *table;             // [table_size] hash slots (-1 = empty)
     uint32_t table_size;        // power of two
     int32_t *nbr;               // out [hi-lo][4]
+    int32_t *nbr_y;             // out [hi-lo][2] (-y, +y; mask bits 4, 5) or nullptr
     vx_halo_item *halo_items;   // out [4(hi-lo)]  (nullptr: neighbours outside are None)
     uint32_t *halo_count;       // out counter
 };

@@ -7,10 +7,13 @@ use crate::coordinate::ChunkCoord3D;
 use crate::cube::{Cube, CubeType};
 use crate::renderer::instance::InstanceRaw;
 use std::ffi::CStr;
-use std::sync::Arc;
 use voxb200_sys as ffi;
 
-/// One GPU context per process (thread-safe; calls on it are serialised by the library).
+/// One GPU context per PROCESS, created on first use: the reference's signatures
+/// (`Chunk::new(position)`, `create_mesh(&self, device, adjacent_chunks)`, `Frustum::contains(&self, &pos)`,
+/// chunk.rs:21,48-52, frustum_culling.rs:16) stay exactly as they are -- nothing has to be threaded
+/// through the worker closures of chunk_builder.rs:80-84,105-108,125-129.  libvoxb200 is thread-safe:
+/// one-chunk calls from the uvth pool threads lease scratch lanes inside the context and overlap.
 pub struct B200 {
     ctx: *mut ffi::vx_ctx,
 }
@@ -25,17 +28,16 @@ fn check(rc: i32) {
     }
 }
 
-impl B200 {
-    pub fn new() -> Arc<Self> {
+static GPU: std::sync::OnceLock<B200> = std::sync::OnceLock::new();
+
+/// The process-global context (`vx_create(NULL, 0)`: every GPU of the box).  Never destroyed: it lives as
+/// long as the process, like `graphics.device`.
+pub fn gpu() -> &'static B200 {
+    GPU.get_or_init(|| {
         let mut ctx = std::ptr::null_mut();
-        check(unsafe { ffi::vx_create(std::ptr::null(), 0, &mut ctx) }); // 0 = every GPU of the box
-        Arc::new(Self { ctx })
-    }
-}
-impl Drop for B200 {
-    fn drop(&mut self) {
-        unsafe { ffi::vx_destroy(self.ctx) }
-    }
+        check(unsafe { ffi::vx_create(std::ptr::null(), 0, &mut ctx) });
+        B200 { ctx }
+    })
 }
 
 fn cube_from_id(id: u8) -> Cube {
@@ -48,7 +50,8 @@ fn cube_from_id(id: u8) -> Cube {
 
 /// Body of `Chunk::generate_terrain` (chunk.rs:27-46): replaces the simdnoise call and the
 /// threshold loop.  `cubes` ends up in the same idx order (x + 32 z + 1024 y).
-pub fn generate_terrain(gpu: &B200, cubes: &mut Vec<Cube>, pos: ChunkCoord3D) {
+pub fn generate_terrain(cubes: &mut Vec<Cube>, pos: ChunkCoord3D) {
+    let gpu = gpu();
     let coords = [pos.x, pos.y, pos.z];
     let mut ids = vec![0u8; ffi::VX_VOXELS];
     check(unsafe {
@@ -61,8 +64,9 @@ pub fn generate_terrain(gpu: &B200, cubes: &mut Vec<Cube>, pos: ChunkCoord3D) {
 /// Body of `Chunk::create_mesh` up to the wgpu upload (chunk.rs:48-57, 254-260): returns the
 /// `Vec<InstanceRaw>` that `ChunkMesh::new` hands to `create_buffer_init`.
 /// `own` / `adjacent` are the CubeType bytes of the chunk and of its -x,+x,-z,+z neighbours.
-pub fn create_mesh_instances(gpu: &B200, pos: ChunkCoord3D, own: &[u8],
+pub fn create_mesh_instances(pos: ChunkCoord3D, own: &[u8],
                              adjacent: [Option<(ChunkCoord3D, &[u8])>; 4]) -> Vec<InstanceRaw> {
+    let gpu = gpu();
     let mut coords = vec![pos.x, pos.y, pos.z];
     let mut blocks = own.to_vec();
     let mut nbr = [-1i32; 4];
@@ -92,23 +96,32 @@ pub fn create_mesh_instances(gpu: &B200, pos: ChunkCoord3D, own: &[u8],
 /// The fast path: the worker closure of chunk_builder.rs:80-84 for a whole coordinate list in
 /// one call (noise + meshing on the GPU, instances back through pinned double-buffered D2H).
 /// Returns per-chunk (cube ids, instances).  `nbr_mask[i]` bit k = neighbour k counts as loaded.
-pub fn build_chunks(gpu: &B200, positions: &[ChunkCoord3D], nbr_mask: Option<&[u8]>)
-                    -> Vec<(Vec<u8>, Vec<InstanceRaw>)> {
+/// ONE pass: the instance buffer is sized from the terrain's typical density and the call is repeated
+/// only if the library answers VX_ERR_CAPACITY (counts, offsets and the exact total are valid then).
+pub fn build_chunks(positions: &[ChunkCoord3D], nbr_mask: Option<&[u8]>) -> Vec<(Vec<u8>, Vec<InstanceRaw>)> {
+    let gpu = gpu();
     let n = positions.len();
     let coords: Vec<i32> = positions.iter().flat_map(|p| vec![p.x, p.y, p.z]).collect();
     let mask_ptr = nbr_mask.map_or(std::ptr::null(), |m| m.as_ptr());
     let (mut counts, mut offsets, mut total) = (vec![0u32; n], vec![0u64; n + 1], 0u64);
-    check(unsafe {
-        ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
-                         offsets.as_mut_ptr(), std::ptr::null_mut(), 0, &mut total, std::ptr::null_mut())
-    });
-    let mut inst: Vec<InstanceRaw> = Vec::with_capacity(total as usize);
     let mut blocks = vec![0u8; n * ffi::VX_VOXELS];
-    check(unsafe {
-        ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
-                         offsets.as_mut_ptr(), inst.as_mut_ptr() as *mut ffi::vx_instance, total as usize,
-                         &mut total, blocks.as_mut_ptr())
-    });
+    // default terrain: ~4.6 k quads per chunk with neighbours, at most ~7.9 k without
+    let mut cap = n * 8192;
+    let mut inst: Vec<InstanceRaw> = Vec::with_capacity(cap);
+    loop {
+        let rc = unsafe {
+            ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
+                             offsets.as_mut_ptr(), inst.as_mut_ptr() as *mut ffi::vx_instance, cap, &mut total,
+                             blocks.as_mut_ptr())
+        };
+        if rc == ffi::VX_ERR_CAPACITY {
+            cap = total as usize; // exact now
+            inst = Vec::with_capacity(cap);
+            continue;
+        }
+        check(rc);
+        break;
+    }
     unsafe { inst.set_len(total as usize) };
     (0..n).map(|i| {
         (blocks[i * ffi::VX_VOXELS..(i + 1) * ffi::VX_VOXELS].to_vec(),
@@ -125,7 +138,8 @@ pub fn matrix_to_planes(m: &[f32; 16]) -> [f32; 24] {
 
 /// `Frustum::contains` (frustum_culling.rs:16-40) for a whole list in one launch; use it at
 /// chunk_builder.rs:217-255 (enqueue gate) and world.rs:34-37 (draw gate).
-pub fn frustum_contains_many(gpu: &B200, planes: &[f32; 24], positions: &[ChunkCoord3D]) -> Vec<bool> {
+pub fn frustum_contains_many(planes: &[f32; 24], positions: &[ChunkCoord3D]) -> Vec<bool> {
+    let gpu = gpu();
     let coords: Vec<i32> = positions.iter().flat_map(|p| vec![p.x, p.y, p.z]).collect();
     let mut vis = vec![0u8; positions.len()];
     check(unsafe {

@@ -33,6 +33,14 @@ pub struct vx_noise_params {
     pub simplex_scale: f32,
 }
 
+/// extension: vertical neighbours + DIRT rule, see voxb200.h
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct vx_terrain_opts {
+    pub vertical_neighbours: u32,
+    pub dirt_rule: u32,
+}
+
 /// renderer/instance.rs:1-6 `InstanceRaw` (68 bytes, `#[repr(C)]`) -- same layout, so a
 /// `&[vx_instance]` can be `bytemuck::cast_slice`d straight into `create_buffer_init`.
 #[repr(C)]
@@ -87,6 +95,14 @@ extern "C" {
                               blocks_out: *mut u8, stream: *mut c_void) -> c_int;
     pub fn vx_frustum_cull_device(ctx: *mut vx_ctx, planes: *const f32, n_frames: usize, coords: *const i32,
                                   n: usize, visible: *mut u8, bits: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn vx_gen_mesh_ex(ctx: *mut vx_ctx, coords: *const i32, n: usize, params: *const vx_noise_params,
+                          opts: *const vx_terrain_opts, nbr_mask: *const u8, counts: *mut u32, offsets: *mut u64,
+                          instances: *mut vx_instance, capacity: usize, total_out: *mut u64,
+                          blocks_out: *mut u8) -> c_int;
+    pub fn vx_gen_mesh_ex_device(ctx: *mut vx_ctx, coords: *const i32, n: usize, params: *const vx_noise_params,
+                                 opts: *const vx_terrain_opts, nbr_mask: *const u8, counts: *mut u32,
+                                 offsets: *mut u64, instances: *mut vx_instance, capacity: usize,
+                                 status: *mut u32, blocks_out: *mut u8, stream: *mut c_void) -> c_int;
     pub fn vx_emit_again_device(ctx: *mut vx_ctx, coords: *const i32, n: usize, counts: *mut u32,
                                 offsets: *mut u64, instances: *mut vx_instance, capacity: usize,
                                 status: *mut u32, stream: *mut c_void) -> c_int;

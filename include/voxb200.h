@@ -129,7 +129,8 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
  * emission order ((y,z,x)-major, then LEFT,RIGHT,BACK,FRONT,DOWN,UP).
  * instances may be NULL (count only).  total_out receives offsets[n].
  * An nbr_idx entry >= n is VX_ERR_BAD_ARG (checked before anything is enqueued).
- * (Runs on the context's first GPU: the call is PCIe-bound on the 32 KiB/chunk upload.) */
+ * With several GPUs in the context, lists of more than 32 chunks are split by contiguous index range; a
+ * device also receives the out-of-range chunks its own chunks name as neighbours (mesh-less ghosts). */
 int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
             const int32_t *nbr_idx, const uint8_t *mesh_mask,
             uint32_t *counts, uint64_t *offsets,

@@ -338,6 +338,24 @@ def test_multi_gpu_context_equals_single(ctx, vox):
         f1 = ctx.fill(coords, noise=True)
         f2 = c2.fill(coords, noise=True)
         assert np.array_equal(f1["noise"], f2["noise"])
+        # vx_mesh over two GPUs (ghost chunks for the neighbours across the cut): by-coordinate lookup, explicit
+        # wiring with a mesh mask, and the vertical-neighbour extension through the fused call
+        m1 = ctx.mesh(coords, one.blocks)
+        m2 = c2.mesh(coords, one.blocks)
+        assert np.array_equal(m1.counts, m2.counts) and m1.instances.tobytes() == m2.instances.tobytes()
+        assert m1.instances.tobytes() == one.instances.tobytes()
+        rng = np.random.default_rng(2)
+        n = len(coords)
+        wiring = rng.integers(-1, n, size=(n, 4)).astype(np.int32)
+        mask = (rng.random(n) < 0.7).astype(np.uint8)
+        blocks = rng.choice(np.array([0, 1, 2], np.uint8), size=(n, 32768), p=[0.4, 0.1, 0.5])
+        w1 = ctx.mesh(coords, blocks, nbr_idx=wiring, mesh_mask=mask)
+        w2 = c2.mesh(coords, blocks, nbr_idx=wiring, mesh_mask=mask)
+        assert np.array_equal(w1.counts, w2.counts) and w1.instances.tobytes() == w2.instances.tobytes()
+        st = np.array([(x, y, z) for y in (0, 1) for z in range(6) for x in range(6)], np.int32)
+        e1 = ctx.gen_mesh(st, blocks=True, vertical=True, dirt_rule=True)
+        e2 = c2.gen_mesh(st, blocks=True, vertical=True, dirt_rule=True)
+        assert np.array_equal(e1.blocks, e2.blocks) and e1.instances.tobytes() == e2.instances.tobytes()
 
 
 def test_cpp_host_mirror_matches_oracle(vox, oracle, tmp_path):

@@ -28,4 +28,17 @@ mm = ctx.mesh(coords[:2], np.stack([cb, r.blocks[0]]))                   # pack,
 planes = np.random.default_rng(0).standard_normal((70, 6, 4)).astype(np.float32)
 v = ctx.frustum_cull(planes, coords)
 b = ctx.frustum_cull(planes, coords, bits=True)
-print("ok", r.total, r2.total, f["near_zero"], mm.total, int(v.sum()), ctx.launch_count)
+# single-frame kernel (G = 1; ragged tail) and its two-groups-per-thread form (> 606 k chunks)
+big = np.zeros((700003, 3), np.int32)
+big[:, 0] = np.arange(700003) % 997 - 400
+big[:, 2] = np.arange(700003) // 997 - 300
+v1 = ctx.frustum_cull(planes[:1], coords[:13])
+b1 = ctx.frustum_cull(planes[:1], big, bits=True)
+v2 = ctx.frustum_cull(planes[:1], big)
+assert int(np.unpackbits(b1.view(np.uint8), bitorder="little")[:700003].sum()) == int(v2.sum())
+# extension: vertical neighbours (in-list, halo y planes) + DIRT rule, blocks from the occupancy planes
+st = np.array([(x, y, 0) for y in (-1, 0, 1) for x in (0, 1)], np.int32)
+e1 = ctx.gen_mesh(st, blocks=True, vertical=True, dirt_rule=True)
+e2 = ctx.gen_mesh(st[:3], nbr_mask=np.full(3, 63, np.uint8), blocks=True, vertical=True, dirt_rule=True)
+f7 = ctx.fill(coords[:2], params=voxb200.default_noise_params(simplex_scale=1.0), blocks=True)   # raw simplex sum
+print("ok", r.total, r2.total, f["near_zero"], mm.total, int(v.sum()), int(v2.sum()), e1.total, e2.total, ctx.launch_count)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--freq", type=float, default=None)
     ap.add_argument("--lacunarity", type=float, default=None)
     ap.add_argument("--gain", type=float, default=None)
+    ap.add_argument("--scale", type=float, default=None, help="vx_noise_params.simplex_scale (default: the library's)")
     ap.add_argument("--origin", default="0,0,0", help="chunk coordinate of the region centre (x,y,z)")
     args = ap.parse_args()
     import torch
@@ -41,7 +42,8 @@ def main():
     occ_exact = torch.zeros(nb * 1024, dtype=torch.int32, device=dev)
     nz = torch.zeros(1, dtype=torch.int64, device=dev)
     for seed in [int(v) for v in args.seeds.split(",")]:
-        kw = {k: v for k, v in (("freq", args.freq), ("lacunarity", args.lacunarity), ("gain", args.gain)) if v is not None}
+        kw = {k: v for k, v in (("freq", args.freq), ("lacunarity", args.lacunarity), ("gain", args.gain),
+                                    ("simplex_scale", args.scale)) if v is not None}
         p = voxb200.default_noise_params(seed=seed, **kw)
         ox, oy, oz = (int(v) for v in args.origin.split(","))
         voxels = mismatched_words = near = solid = 0

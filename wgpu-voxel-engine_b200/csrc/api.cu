@@ -13,6 +13,7 @@
 #include <deque>
 #include <functional>
 #include <thread>
+#include <unordered_map>
 #include <cstdarg>
 #include <cstdio>
 #include <condition_variable>
@@ -733,6 +734,128 @@ int vx_mesh_device(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *
     return VX_OK;
 }
 
+// vx_mesh over several GPUs: the list is split by contiguous index range; every device also receives, as
+// mesh-less "ghost" chunks, the few chunks outside its range that its own chunks name as neighbours (for a
+// contiguous band of a grid: one row on either side), so the device-side mesher needs nothing from its peers.
+static int mesh_multi(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
+                      const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances,
+                      size_t capacity, uint64_t *total_out)
+{
+    const size_t nd = ctx->devs.size();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    // neighbour table of the whole list: the caller's, or looked up by coordinate (chunk_builder.rs:134-169)
+    std::vector<int32_t> nbr_all;
+    if (!nbr_idx) {
+        struct Key { int32_t x, y, z; bool operator==(const Key &o) const { return x == o.x && y == o.y && z == o.z; } };
+        struct KeyHash { size_t operator()(const Key &k) const {
+            return ((uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)k.z * 0xC2B2AE3D27D4EB4Full) ^
+                   ((uint64_t)(uint32_t)k.y * 0xD6E8FEB86659FD93ull); } };
+        std::unordered_map<Key, int32_t, KeyHash> where;
+        where.reserve(n * 2);
+        for (size_t i = 0; i < n; ++i) where.emplace(Key{coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]}, (int32_t)i);   // first wins
+        nbr_all.resize(n * 4);
+        static const int dx[4] = {-1, 1, 0, 0}, dz[4] = {0, 0, -1, 1};
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) {
+                const Key q{(int32_t)((uint32_t)coords[3 * i] + (uint32_t)dx[k]), coords[3 * i + 1],
+                            (int32_t)((uint32_t)coords[3 * i + 2] + (uint32_t)dz[k])};
+                auto it = where.find(q);
+                nbr_all[4 * i + k] = it == where.end() ? -1 : it->second;
+            }
+        nbr_idx = nbr_all.data();
+    }
+    std::vector<uint32_t> lo(nd), hi(nd);
+    std::vector<std::vector<uint64_t>> loc(nd);
+    std::vector<int> bad_block(nd, 0);
+    RET(for_each_device(nd, [&](size_t di) -> int {
+        Dev &d = ctx->devs[di];
+        split_range(n, nd, di, 1, &lo[di], &hi[di]);
+        const uint32_t c = hi[di] - lo[di];
+        if (c == 0) return VX_OK;
+        // local list = own chunks, then ghosts
+        std::vector<int32_t> ghosts;
+        std::unordered_map<int32_t, int32_t> ghost_slot;
+        std::vector<int32_t> l_nbr((size_t)c * 4);
+        for (uint32_t i = 0; i < c; ++i)
+            for (int k = 0; k < 4; ++k) {
+                const int32_t g = nbr_idx[4 * (size_t)(lo[di] + i) + k];
+                int32_t l = -1;
+                if (g >= 0) {
+                    if ((uint32_t)g >= lo[di] && (uint32_t)g < hi[di]) l = g - (int32_t)lo[di];
+                    else {
+                        auto it = ghost_slot.find(g);
+                        if (it == ghost_slot.end()) {
+                            it = ghost_slot.emplace(g, (int32_t)(c + ghosts.size())).first;
+                            ghosts.push_back(g);
+                        }
+                        l = it->second;
+                    }
+                }
+                l_nbr[4 * (size_t)i + k] = l;
+            }
+        const size_t m = (size_t)c + ghosts.size();
+        l_nbr.resize(m * 4, -1);
+        std::vector<int32_t> l_coords(m * 3);
+        std::memcpy(l_coords.data(), coords + 3 * (size_t)lo[di], (size_t)c * 12);
+        std::vector<uint8_t> l_mask(m, 0);
+        for (uint32_t i = 0; i < c; ++i) l_mask[i] = mesh_mask ? mesh_mask[lo[di] + i] : 1;
+        for (size_t j = 0; j < ghosts.size(); ++j) std::memcpy(&l_coords[3 * (c + j)], coords + 3 * (size_t)ghosts[j], 12);
+        CK(cudaSetDevice(d.id));
+        cudaStream_t s = d.stream;
+        CK(d.coords.ensure(m * 12));
+        CK(d.blocks.ensure(m * VX_VOXELS));
+        CK(d.counts.ensure(m * 4));
+        CK(d.offsets.ensure((m + 1) * 8));
+        CK(d.nbr_in.ensure(m * 16));
+        CK(d.mesh_mask.ensure(m));
+        CK(cudaMemcpyAsync(d.coords.p, l_coords.data(), m * 12, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.blocks.p, blocks + (size_t)lo[di] * VX_VOXELS, (size_t)c * VX_VOXELS, cudaMemcpyHostToDevice, s));
+        for (size_t j = 0; j < ghosts.size(); ++j)
+            CK(cudaMemcpyAsync(d.blocks.as<uint8_t>() + (c + j) * VX_VOXELS, blocks + (size_t)ghosts[j] * VX_VOXELS,
+                               VX_VOXELS, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.nbr_in.p, l_nbr.data(), m * 16, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.mesh_mask.p, l_mask.data(), m, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d.st(), 0, 4, s));
+        RET(mesh_prepare(d, s, d.coords.as<int32_t>(), (uint32_t)m, d.blocks.as<uint8_t>(), d.nbr_in.as<int32_t>(),
+                         d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), d.mesh_mask.as<uint8_t>(), d.st()));
+        loc[di].resize((size_t)c + 1);
+        CK(cudaMemcpyAsync(counts + lo[di], d.counts.p, (size_t)c * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(loc[di].data(), d.offsets.p, ((size_t)c + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(d.h_small, d.st(), 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));               // (the host vectors above must outlive the copies)
+        bad_block[di] = (d.h_small[0] & VX_ST_BAD_BLOCK) ? 1 : 0;
+        return VX_OK;
+    }));
+    for (size_t di = 0; di < nd; ++di)
+        if (bad_block[di])
+            return fail(VX_ERR_BAD_BLOCK, "blocks contain an id outside {0 GRASS, 1 DIRT, 2 AIR} (cube.rs:16-21)");
+    uint64_t total = 0;
+    std::vector<uint64_t> base(nd, 0);
+    for (size_t di = 0; di < nd; ++di) {
+        const uint32_t c = hi[di] - lo[di];
+        if (c == 0) continue;
+        base[di] = total;
+        for (uint32_t i = 0; i < c; ++i) offsets[lo[di] + i] = total + loc[di][i];
+        total += loc[di][c];
+    }
+    offsets[n] = total;
+    if (total_out) *total_out = total;
+    if (!instances) return VX_OK;
+    if (total > capacity)
+        return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
+    return for_each_device(nd, [&](size_t di) -> int {
+        const uint32_t c = hi[di] - lo[di];
+        if (c == 0) return VX_OK;
+        Dev &d = ctx->devs[di];
+        CK(cudaSetDevice(d.id));
+        // ghosts sit behind the own chunks and have count 0: emitting the first c chunks is the whole shard
+        vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), d.typ.as<uint32_t>(), d.mesh_mask.as<uint8_t>(),
+                                   d.counts.as<uint32_t>(), d.offsets.as<uint64_t>(), c);
+        RET(dev_stream_instances(d, m, loc[di].data(), c, reinterpret_cast<unsigned char *>(instances) + base[di] * sizeof(vx_instance)));
+        return sync_dev(d);
+    });
+}
+
 int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
             const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances, size_t capacity,
             uint64_t *total_out)
@@ -746,6 +869,8 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
     if (nbr_idx)        // validated before anything is enqueued
         for (size_t i = 0; i < n * 4; ++i)
             if (nbr_idx[i] >= (int64_t)n) return fail(VX_ERR_BAD_ARG, "nbr_idx[%zu] = %d out of range", i, nbr_idx[i]);
+    if (ctx->devs.size() > 1 && n > kShortList)
+        return mesh_multi(ctx, coords, n, blocks, nbr_idx, mesh_mask, counts, offsets, instances, capacity, total_out);
     DevGuard guard(ctx, n);
     if (!guard.d) return cuda_fail(guard.err, "lane setup", __LINE__);
     Dev &d = *guard.d;

@@ -13,6 +13,43 @@
 
 namespace {
 
+// One plane against the eight corners of one AABB.  The reference evaluates ((a*x + b*y) + c*z) + d with every
+// product and sum rounded separately (frustum_culling.rs:29-32); the six products are shared by the corners, and
+// the 20 additions run as 10 packed FADD2 (sm_100: two IEEE-rn sums per issue slot) on the (x0, x1) corner pairs.
+// Every product stays a SCALAR __fmul_rn: ptxas contracts a packed product into a packed add that consumes it
+// (FFMA2) even where contraction is off, and does not fuse across the scalar / packed boundary.
+//   m[0..3] = running minima of the pairs (000,100) (001,101) (010,110) (011,111)   [xyz bits as in :19-26]
+__device__ __forceinline__ void plane_dist(const float4 pl, float x0, float x1, float y0, float y1, float z0, float z1,
+                                           float2 (&t)[4])
+{
+    const float2 ax = make_float2(__fmul_rn(pl.x, x0), __fmul_rn(pl.x, x1));
+    const float by0 = __fmul_rn(pl.y, y0), by1 = __fmul_rn(pl.y, y1);
+    const float cz0 = __fmul_rn(pl.z, z0), cz1 = __fmul_rn(pl.z, z1);
+    const float2 s0 = __fadd2_rn(ax, make_float2(by0, by0)), s1 = __fadd2_rn(ax, make_float2(by1, by1));
+    const float2 d = make_float2(pl.w, pl.w);
+    const float2 t00 = __fadd2_rn(__fadd2_rn(s0, make_float2(cz0, cz0)), d);      // corners (x, y0, z0)
+    const float2 t01 = __fadd2_rn(__fadd2_rn(s0, make_float2(cz1, cz1)), d);      // (x, y0, z1)
+    const float2 t10 = __fadd2_rn(__fadd2_rn(s1, make_float2(cz0, cz0)), d);      // (x, y1, z0)
+    const float2 t11 = __fadd2_rn(__fadd2_rn(s1, make_float2(cz1, cz1)), d);      // (x, y1, z1)
+    t[0] = t00; t[1] = t01; t[2] = t10; t[3] = t11;
+}
+// two planes per step: min(min(m, a), b) is one three-input FMNMX3 on sm_100.  fminf ignores a NaN operand, which
+// is the reference's behaviour (a NaN distance never rejects, :33)
+__device__ __forceinline__ void plane_pair_step(const float4 pa, const float4 pb, float x0, float x1, float y0, float y1,
+                                                float z0, float z1, float2 (&m)[4])
+{
+    float2 ta[4], tb[4];
+    plane_dist(pa, x0, x1, y0, y1, z0, z1, ta);
+    plane_dist(pb, x0, x1, y0, y1, z0, z1, tb);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        m[c] = make_float2(fminf(fminf(m[c].x, ta[c].x), tb[c].x), fminf(fminf(m[c].y, ta[c].y), tb[c].y));
+}
+__device__ __forceinline__ float best_corner(const float2 (&m)[4])
+{
+    return fmaxf(fmaxf(fmaxf(m[0].x, m[0].y), fmaxf(m[1].x, m[1].y)), fmaxf(fmaxf(m[2].x, m[2].y), fmaxf(m[3].x, m[3].y)));
+}
+
 constexpr int kThreads = 256;
 constexpr int kFramesPerCta = 64;
 
@@ -46,36 +83,21 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
         // planes iff that minimum is not < 0.  fminf ignores a NaN operand, which is the
         // reference's behaviour (a NaN distance never rejects, frustum_culling.rs:33).
         const float inf = __int_as_float(0x7f800000);
-        float m0 = inf, m1 = inf, m2 = inf, m3 = inf, m4 = inf, m5 = inf, m6 = inf, m7 = inf;
+        float2 m[4] = {make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf)};
         bool dead = false;
 #pragma unroll
-        for (uint32_t p = 0; p < 6; ++p) {
-            const float4 pl = s_pl[f * 6 + p];
-            const float ax0 = __fmul_rn(pl.x, x0), ax1 = __fmul_rn(pl.x, x1);
-            const float by0 = __fmul_rn(pl.y, y0), by1 = __fmul_rn(pl.y, y1);
-            const float cz0 = __fmul_rn(pl.z, z0), cz1 = __fmul_rn(pl.z, z1);
-            const float s00 = __fadd_rn(ax0, by0), s10 = __fadd_rn(ax1, by0);
-            const float s01 = __fadd_rn(ax0, by1), s11 = __fadd_rn(ax1, by1);
-            m0 = fminf(m0, __fadd_rn(__fadd_rn(s00, cz0), pl.w));
-            m1 = fminf(m1, __fadd_rn(__fadd_rn(s10, cz0), pl.w));
-            m2 = fminf(m2, __fadd_rn(__fadd_rn(s00, cz1), pl.w));
-            m3 = fminf(m3, __fadd_rn(__fadd_rn(s10, cz1), pl.w));
-            m4 = fminf(m4, __fadd_rn(__fadd_rn(s01, cz0), pl.w));
-            m5 = fminf(m5, __fadd_rn(__fadd_rn(s11, cz0), pl.w));
-            m6 = fminf(m6, __fadd_rn(__fadd_rn(s01, cz1), pl.w));
-            m7 = fminf(m7, __fadd_rn(__fadd_rn(s11, cz1), pl.w));
+        for (uint32_t p = 1; p < 6; p += 2) {
+            plane_pair_step(s_pl[f * 6 + p - 1], s_pl[f * 6 + p], x0, x1, y0, y1, z0, z1, m);
             if (p == 1 || p == 3) {
                 // the result is a pure function, so the remaining planes can be skipped once no
                 // lane of the warp has a live corner
-                const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-                if (!__any_sync(VX_FULL, live && !(best < 0.0f))) {
+                if (!__any_sync(VX_FULL, live && !(best_corner(m) < 0.0f))) {
                     dead = true;
                     break;
                 }
             }
         }
-        const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-        const bool vis = live && !dead && !(best < 0.0f);
+        const bool vis = live && !dead && !(best_corner(m) < 0.0f);
         const uint32_t word = __ballot_sync(VX_FULL, vis);
         if (WANT_BYTES && live) visible[(size_t)(f0 + f) * n + i] = vis ? 1 : 0;
         if (WANT_BITS && (threadIdx.x & 31) == 0 && live) bits[(size_t)(f0 + f) * n_words + (i >> 5)] = word;
@@ -96,29 +118,15 @@ __device__ __forceinline__ bool aabb_visible(const float4 (&pl)[6], int32_t cx, 
                 z0 = (float)(int32_t)((uint32_t)cz * 32u);
     const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
     const float inf = __int_as_float(0x7f800000);
-    float m0 = inf, m1 = inf, m2 = inf, m3 = inf, m4 = inf, m5 = inf, m6 = inf, m7 = inf;
+    float2 m[4] = {make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf)};
 #pragma unroll
-    for (uint32_t p = 0; p < 6; ++p) {
-        const float ax0 = __fmul_rn(pl[p].x, x0), ax1 = __fmul_rn(pl[p].x, x1);
-        const float by0 = __fmul_rn(pl[p].y, y0), by1 = __fmul_rn(pl[p].y, y1);
-        const float cz0 = __fmul_rn(pl[p].z, z0), cz1 = __fmul_rn(pl[p].z, z1);
-        const float s00 = __fadd_rn(ax0, by0), s10 = __fadd_rn(ax1, by0);
-        const float s01 = __fadd_rn(ax0, by1), s11 = __fadd_rn(ax1, by1);
-        m0 = fminf(m0, __fadd_rn(__fadd_rn(s00, cz0), pl[p].w));
-        m1 = fminf(m1, __fadd_rn(__fadd_rn(s10, cz0), pl[p].w));
-        m2 = fminf(m2, __fadd_rn(__fadd_rn(s00, cz1), pl[p].w));
-        m3 = fminf(m3, __fadd_rn(__fadd_rn(s10, cz1), pl[p].w));
-        m4 = fminf(m4, __fadd_rn(__fadd_rn(s01, cz0), pl[p].w));
-        m5 = fminf(m5, __fadd_rn(__fadd_rn(s11, cz0), pl[p].w));
-        m6 = fminf(m6, __fadd_rn(__fadd_rn(s01, cz1), pl[p].w));
-        m7 = fminf(m7, __fadd_rn(__fadd_rn(s11, cz1), pl[p].w));
+    for (uint32_t p = 1; p < 6; p += 2) {
+        plane_pair_step(pl[p - 1], pl[p], x0, x1, y0, y1, z0, z1, m);
         if (p == 1 || p == 3) {
-            const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-            if (!__any_sync(VX_FULL, live && !(best < 0.0f))) return false;
+            if (!__any_sync(VX_FULL, live && !(best_corner(m) < 0.0f))) return false;
         }
     }
-    const float best = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-    return live && !(best < 0.0f);
+    return live && !(best_corner(m) < 0.0f);
 }
 
 // G groups of four chunks per thread (group g of round r = r * threads + thread: every round is a

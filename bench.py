@@ -378,6 +378,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms_one_stream, _, _, _ = timed(lambda: band.region_pass(lanes=1), 1, max(1, min(K, 3)), 1)
     value_one_stream = R * R * max(1, min(K, 3)) / (ms_one_stream * 1e-3)
 
+    if args.device_only:
+        if rank == 0:
+            emit_json({"value": value, "ms_per_step": ms_total / K, "one_stream": value_one_stream, "n_gpus": world,
+                       "env": {k: v for k, v in os.environ.items() if k.startswith("VX_")}})
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---- untimed digest pass: per-chunk counts of the whole band, status words --------------------------------
     band.region_pass(record=True)
     torch.cuda.synchronize()
@@ -706,6 +714,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--region", type=int, default=REGION, help="edge of the square region in chunks (tests use less)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="A/B aid: only the device-timed region passes, a short line (not the driver's contract)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

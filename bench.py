@@ -287,7 +287,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # Two contexts and two streams on the GPU, batches alternate between them: each context owns its scratch
     # and output arena, so the HBM-bound emit of batch i overlaps the issue-bound fill of batch i + 1
     # (what a host does with two batches in flight).
-    PIPE = 2
+    PIPE = int(os.environ.get("VX_BENCH_PIPE", "2"))       # (experiments only; the reported configuration is 2)
     ctxs = [voxb200.Context(devices=[local_rank]) for _ in range(PIPE)]
     ctx = ctxs[0]
     d_counts_l = [torch.zeros(nb, dtype=torch.int32, device=dev) for _ in range(PIPE)]

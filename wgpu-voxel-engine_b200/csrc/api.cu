@@ -91,8 +91,7 @@ constexpr size_t kStageBytes = 4096;                                   // >= kSh
 struct Dev {
     int id = 0;
     int n_sm = 148;
-    cudaStream_t stream = nullptr, copy = nullptr, aux = nullptr, emit_hi = nullptr;
-    cudaEvent_t emit_fork = nullptr, emit_join = nullptr;
+    cudaStream_t stream = nullptr, copy = nullptr, aux = nullptr;
     cudaEvent_t emit_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;   // aux stream: neighbour resolve + halo fill beside the main fill
     DevBuf coords, mask8, occ, typ, halo, halo_items, table, nbr, nbr_y, nbr_in, counts, offsets, small, blocks, noise,
@@ -351,13 +350,6 @@ cudaError_t init_dev(Dev &d, int id)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking);
-    if (e == cudaSuccess) {
-        int lo_p = 0, hi_p = 0;
-        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);      // hi_p = numerically lowest = highest priority
-        e = cudaStreamCreateWithPriority(&d.emit_hi, cudaStreamNonBlocking, hi_p);
-    }
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.emit_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.emit_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
@@ -393,9 +385,6 @@ void destroy_dev(Dev &d)
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy) cudaStreamDestroy(d.copy);
     if (d.aux) cudaStreamDestroy(d.aux);
-    if (d.emit_hi) cudaStreamDestroy(d.emit_hi);
-    if (d.emit_fork) cudaEventDestroy(d.emit_fork);
-    if (d.emit_join) cudaEventDestroy(d.emit_join);
     if (d.fork) cudaEventDestroy(d.fork);
     if (d.join) cudaEventDestroy(d.join);
 }
@@ -961,19 +950,7 @@ static int gen_mesh_device_impl(vx_ctx *ctx, const int32_t *coords, size_t n, co
         m.packed = packed ? 1 : 0;
         m.capacity = capacity;
         m.status = status;
-        // EXPERIMENT (VX_EMIT_BG_SMEM = bytes): the emit runs on a high-priority stream with its shared-memory request
-        // padded so that only 1 (114 KB) or 2 (80 KB) of its CTAs fit an SM beside 3 / 2 CTAs of another context's fill
-        static const size_t bg = [] { const char *e = getenv("VX_EMIT_BG_SMEM"); return e ? (size_t)atol(e) : 0; }();
-        if (bg && !packed) {
-            m.smem_pad = bg;
-            CK(cudaEventRecord(d.emit_fork, s));
-            CK(cudaStreamWaitEvent(d.emit_hi, d.emit_fork, 0));
-            TIMED(d, d.emit_hi, VX_K_EMIT, vx_launch_mesh_emit(m, nn, d.emit_hi, &d.launches));
-            CK(cudaEventRecord(d.emit_join, d.emit_hi));
-            CK(cudaStreamWaitEvent(s, d.emit_join, 0));
-        } else {
-            TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
-        }
+        TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
     }
     return VX_OK;
 }

@@ -15,7 +15,6 @@
 // (y,z,x) order, faces LEFT,RIGHT,BACK,FRONT,DOWN,UP -- an exclusive scan of
 // per-row counts keeps that order, so parity is a plain compare.
 // The emit kernel is HBM-write bound (68 B per quad).
-#include <algorithm>
 #include <cstddef>
 
 #include "vx_common.cuh"
@@ -762,7 +761,7 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
         if (a.packed)
             vx_mesh_emit_kernel<true, 1><<<len, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
         else
-            vx_mesh_emit_kernel<false, 1><<<len, kEmitThreads, std::max<size_t>(sizeof(EmitSmem), a.smem_pad), s>>>(a);
+            vx_mesh_emit_kernel<false, 1><<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     }
     if (launches) ++*launches;
     return cudaGetLastError();
@@ -772,13 +771,13 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
 // the device current.
 cudaError_t vx_init_mesh_kernels()
 {
-    // (up to the whole SM: a background emit pads its request to cap its own residency, see vx_mesh_args.smem_pad)
     cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+                                         (int)sizeof(EmitSmem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, kEmitSplitSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(EmitSmem));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));
+    e = cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));
+    return e;
 }

@@ -62,8 +62,6 @@ struct vx_mesh_args {
     uint32_t n;
     uint32_t m0;                // emit: first chunk of this launch
     unsigned long long quad_base;   // emit: offsets value that maps to out[0]
-    size_t smem_pad;            // emit (host only): request at least this much dynamic shared memory, to cap how many
-                                // emit CTAs share an SM with a concurrently running fill (0 = no padding)
 };
 cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t *launches);
 cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches);

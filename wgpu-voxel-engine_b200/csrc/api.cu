@@ -98,7 +98,7 @@ struct Dev {
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
-    uint64_t launches = 0;
+    vx_counter launches{0};
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
     bool ex_vertical = false;      // extension state of the current batch (vx_terrain_opts): nbr_y is valid
@@ -551,9 +551,9 @@ uint64_t vx_launch_count(const vx_ctx *ctx)
 {
     uint64_t t = 0;
     if (ctx) {
-        for (const Dev &d : ctx->devs) t += d.launches;
+        for (const Dev &d : ctx->devs) t += d.launches.load(std::memory_order_relaxed);
         std::lock_guard<std::mutex> lk(const_cast<vx_ctx *>(ctx)->lane_mu);
-        for (const auto &l : ctx->lanes) t += l->launches;
+        for (const auto &l : ctx->lanes) t += l->launches.load(std::memory_order_relaxed);
     }
     return t;
 }

@@ -548,10 +548,10 @@ cudaError_t launch_oct(const vx_fill_args &a, cudaStream_t s)
 
 }  // namespace
 
-cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, vx_counter *launches)
 {
     if (a.max_units == 0) return cudaSuccess;
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     // octaves = 3 (perlin_noise.rs:18) without noise/census output: sign-only brick kernel
     // (the coefficient-table gradient multiplies by 0, so coordinates must stay finite:
     //  |world * freq * lac^k| <= 2^31 * |freq| * max(1, lac^2) must not overflow f32)

@@ -192,7 +192,7 @@ void launch_one(const float *planes, const int32_t *coords, uint32_t n, uint8_t 
 }  // namespace
 
 cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
-                              uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches)
+                              uint8_t *visible, uint32_t *bits, cudaStream_t s, vx_counter *launches)
 {
     if (n == 0 || n_frames == 0) return cudaSuccess;
     if (n_frames == 1 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15u) == 0 &&
@@ -200,7 +200,7 @@ cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int3
         // one wave if possible: 148 SMs x 4 resident CTAs x 256 threads x 4 chunks = 606 k chunks with G = 1
         if (n <= 148u * 4u * kThreads * 4u) launch_one<1>(planes, coords, n, visible, bits, s);
         else launch_one<2>(planes, coords, n, visible, bits, s);
-        if (launches) ++*launches;
+        if (launches) launches->fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     }
     const dim3 grid((n + kThreads - 1) / kThreads, (n_frames + kFramesPerCta - 1) / kFramesPerCta);
@@ -211,6 +211,6 @@ cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int3
         vx_frustum_kernel<true, false><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);
     else
         vx_frustum_kernel<false, true><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -229,7 +229,7 @@ struct RowFaces {
     uint32_t m[6];      // LEFT, RIGHT, BACK, FRONT, DOWN, UP
 };
 
-struct ChunkSmem {
+struct __align__(16) ChunkSmem {
     uint32_t occ[VX_ROWS + 64];   // rows -32..-1 and 1024..1055 are zero (y borders always emit)
     uint32_t back[32];            // -z neighbour: row (y, 31) per y, or 0
     uint32_t front[32];           // +z neighbour: row (y, 0) per y, or 0
@@ -309,6 +309,31 @@ __device__ __forceinline__ RowFaces row_faces(const ChunkSmem &s, uint32_t r)
     return f;
 }
 
+// Face masks of the four consecutive rows 4t .. 4t+3 (same y, z = z0 .. z0+3) for the per-chunk row scan: the rows
+// themselves and the rows below / above arrive as three 128-bit shared loads instead of 4 x 7 scalar loads at a
+// stride of four words (a 4-way bank conflict: the 12 % of conflicting wavefronts ncu still showed in round 2).
+__device__ __forceinline__ void row_faces4(const ChunkSmem &s, uint32_t t, RowFaces (&f)[4])
+{
+    const uint32_t r0 = 4u * t, y = r0 >> 5, z0 = r0 & 31u;
+    const uint4 o4 = *reinterpret_cast<const uint4 *>(&s.occ[32 + r0]);
+    const uint4 d4 = *reinterpret_cast<const uint4 *>(&s.occ[r0]);              // rows r - 32
+    const uint4 u4 = *reinterpret_cast<const uint4 *>(&s.occ[64 + r0]);         // rows r + 32
+    const uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w}, dn[4] = {d4.x, d4.y, d4.z, d4.w}, up[4] = {u4.x, u4.y, u4.z, u4.w};
+    const uint32_t before = (z0 > 0u) ? s.occ[32 + r0 - 1] : s.back[y];
+    const uint32_t after = (z0 < 28u) ? s.occ[32 + r0 + 4] : s.front[y];
+    const uint32_t xm = s.xm[y] >> z0, xp = s.xp[y] >> z0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t oj = o[j], bw = j ? o[j - 1] : before, fw = (j < 3u) ? o[j + 1] : after;
+        f[j].m[VX_LEFT] = oj & ~((oj << 1) | ((xm >> j) & 1u));
+        f[j].m[VX_RIGHT] = oj & ~((oj >> 1) | (((xp >> j) & 1u) << 31));
+        f[j].m[VX_BACK] = oj & ~bw;
+        f[j].m[VX_FRONT] = oj & ~fw;
+        f[j].m[VX_DOWN] = oj & ~dn[j];
+        f[j].m[VX_UP] = oj & ~up[j];
+    }
+}
+
 __device__ __forceinline__ uint32_t row_count(const RowFaces &f)
 {
     return __popc(f.m[0]) + __popc(f.m[1]) + __popc(f.m[2]) + __popc(f.m[3]) + __popc(f.m[4]) + __popc(f.m[5]);
@@ -382,8 +407,10 @@ vx_mesh_count_kernel(const vx_mesh_args a)
     }
     stage_chunk<kMeshThreads>(s, a, m);
     uint32_t c = 0;
+    RowFaces f4[4];
+    row_faces4(s, threadIdx.x, f4);
 #pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) c += row_count(row_faces(s, threadIdx.x * 4 + j));
+    for (uint32_t j = 0; j < 4; ++j) c += row_count(f4[j]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(VX_FULL, c, d);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
@@ -550,9 +577,11 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     uint32_t nzc;
     {
         uint32_t cnt[4], mine = 0;
+        RowFaces f4[4];
+        row_faces4(s.c, tid, f4);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
-            cnt[j] = row_count(row_faces(s.c, tid * 4 + j));
+            cnt[j] = row_count(f4[j]);
             mine += cnt[j] + (cnt[j] ? (1u << 20) : 0u);
         }
         uint32_t inc = mine;
@@ -690,16 +719,16 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
 // launchers
 // ---------------------------------------------------------------------------
 cudaError_t vx_launch_pack(const uint8_t *blocks, uint32_t n, uint32_t *occ, uint32_t *typ,
-                           uint32_t *status, cudaStream_t s, uint64_t *launches)
+                           uint32_t *status, cudaStream_t s, vx_counter *launches)
 {
     if (n == 0) return cudaSuccess;
     const size_t total = (size_t)n * (VX_VOXELS / 16);
     vx_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(blocks, n, occ, typ, status);
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
-cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, vx_counter *launches)
 {
     if (a.n == 0 || a.hi <= a.lo) return cudaSuccess;
     if (a.n <= kSmallResolve) {
@@ -708,7 +737,7 @@ cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t
         while (b.table_size < 2 * a.n) b.table_size <<= 1;
         const size_t smem = (size_t)b.table_size * 4 + (size_t)a.n * 12;      // <= 32 KB + 48 KB (vx_init_mesh_kernels)
         vx_resolve_small_kernel<<<1, 1024, smem, s>>>(b);
-        if (launches) ++*launches;
+        if (launches) launches->fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     }
     cudaError_t e = cudaMemsetAsync(a.table, 0xff, sizeof(int32_t) * a.table_size, s);
@@ -719,36 +748,36 @@ cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t
     }
     vx_ht_insert_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a.coords, a.n, a.table, a.table_size - 1);
     vx_resolve_kernel<<<((a.hi - a.lo) * (a.nbr_y ? 6 : 4) + 255) / 256, 256, 0, s>>>(a);
-    if (launches) *launches += 2;
+    if (launches) launches->fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
 cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, uint32_t *status, cudaStream_t s,
-                                uint64_t *launches)
+                                vx_counter *launches)
 {
     if (n == 0) return cudaSuccess;
     vx_remap_nbr_kernel<<<(n * 4 + 255) / 256, 256, 0, s>>>(nbr_in, nbr_out, n * 4, n, status);
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
-cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, vx_counter *launches)
 {
     if (a.n == 0) return cudaSuccess;
     vx_blocks_ex_kernel<<<a.n, kMeshThreads, 0, s>>>(a, blocks);
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
-cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, vx_counter *launches)
 {
     if (a.n == 0) return cudaSuccess;
     vx_mesh_count_kernel<<<a.n, kMeshThreads, 0, s>>>(a);
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
-cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, vx_counter *launches)
 {
     if (len == 0) return cudaSuccess;
     static_assert(sizeof(EmitSmem) <= 64 * 1024, "emit kernel shared memory budget");
@@ -763,7 +792,7 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
         else
             vx_mesh_emit_kernel<false, 1><<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
     }
-    if (launches) ++*launches;
+    if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 

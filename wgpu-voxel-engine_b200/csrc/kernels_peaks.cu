@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) vx_peak_kernel(float *sink, float seedf, 
 
 }  // namespace
 
-cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, uint64_t *launches)
+cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, vx_counter *launches)
 {
     float *sink = nullptr;
     cudaError_t e = cudaMalloc(&sink, 4);
@@ -62,7 +62,7 @@ cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, ui
         cudaEventRecord(t1, s);
         e = cudaEventSynchronize(t1);
         if (e != cudaSuccess) break;
-        if (launches) ++*launches;
+        if (launches) launches->fetch_add(1, std::memory_order_relaxed);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t0, t1);
         // per chain step: kind 0 = 2 FFMA = 4 flop; kind 1 = FMUL + FADD = 2 flop;

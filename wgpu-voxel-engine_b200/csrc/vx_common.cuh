@@ -1,11 +1,15 @@
 // vx_common.cuh -- shared device/host declarations for libvoxb200 (sm_100a).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "../../include/voxb200.h"
 
 #define VX_FULL 0xffffffffu
+
+// kernel-launch counter of a device / lane: bumped by whichever host thread launches, read by vx_launch_count
+typedef std::atomic<uint64_t> vx_counter;
 
 // status word bits written by device code (vx_*_device `status`)
 #define VX_ST_OVERFLOW 1u
@@ -40,7 +44,7 @@ struct vx_fill_args {
     float thr1, thr2;                 // sign-only shortcuts (set by the launcher)
     float err_margin;                 // certified |fused - exact| bound (set by the launcher)
 };
-cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s, vx_counter *launches);
 
 struct vx_mesh_args {
     const uint32_t *occ;        // [items][1024]
@@ -63,12 +67,12 @@ struct vx_mesh_args {
     uint32_t m0;                // emit: first chunk of this launch
     unsigned long long quad_base;   // emit: offsets value that maps to out[0]
 };
-cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, uint64_t *launches);
-cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, vx_counter *launches);
+cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, vx_counter *launches);
 // extension: CubeType bytes from the occupancy planes (+ the DIRT rule); needs the mesh args' nbr_y / halo
-cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_launch_blocks_ex(const vx_mesh_args &a, uint8_t *blocks, cudaStream_t s, vx_counter *launches);
 cudaError_t vx_launch_pack(const uint8_t *blocks, uint32_t n, uint32_t *occ, uint32_t *typ,
-                           uint32_t *status, cudaStream_t s, uint64_t *launches);
+                           uint32_t *status, cudaStream_t s, vx_counter *launches);
 
 struct vx_resolve_args {
     const int32_t *coords;      // [n][3]
@@ -82,13 +86,13 @@ struct vx_resolve_args {
     vx_halo_item *halo_items;   // out [4(hi-lo)]  (nullptr: neighbours outside are None)
     uint32_t *halo_count;       // out counter
 };
-cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_launch_resolve(const vx_resolve_args &a, cudaStream_t s, vx_counter *launches);
 cudaError_t vx_launch_remap_nbr(const int32_t *nbr_in, int32_t *nbr_out, uint32_t n, uint32_t *status, cudaStream_t s,
-                                uint64_t *launches);
+                                vx_counter *launches);
 
 cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int32_t *coords, uint32_t n,
-                              uint8_t *visible, uint32_t *bits, cudaStream_t s, uint64_t *launches);
+                              uint8_t *visible, uint32_t *bits, cudaStream_t s, vx_counter *launches);
 
 cudaError_t vx_init_mesh_kernels();
 
-cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, uint64_t *launches);
+cudaError_t vx_run_peak(int kind, int n_sm, double *tera_ops, cudaStream_t s, vx_counter *launches);

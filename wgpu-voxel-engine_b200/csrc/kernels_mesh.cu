@@ -504,6 +504,7 @@ struct EmitSmem {
                                              // stride-32 gather from nz_base itself is a 32-way bank conflict)
     __align__(16) uint32_t lut[16 * kLutStride];   // [type*8 + face]: 12 rotation words, [16] = texture layer
     uint32_t pos[3][32];                     // f32 bits of world x / y / z per local coordinate
+    uint32_t face_sel[64];                   // [6 face bits of a cube] -> its set faces in order, 3 bits each
     uint32_t warp_tot[kEmitWarps];
     __align__(16) uint32_t stage[kEmitWarps][kStageBufs][kTileWords];   // per-warp staging tiles
 };
@@ -533,7 +534,10 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 // PACKED = true writes one 32-bit quad record instead of the 68-byte instance (extension for
 // renderers that expand in the vertex shader): bits 0-4 x, 5-9 z, 10-14 y (= voxel idx),
 // 15-17 face (VX_LEFT..VX_UP), 18 block type (0 GRASS, 1 DIRT); the chunk is implied by offsets[].
-template <bool PACKED, int kEmitSplit>
+// TYPES: where a quad's block type comes from -- 0: every block is GRASS (the reference's terrain), 1: the caller's
+// DIRT plane (vx_mesh), 2: the DIRT rule of the extension (the voxel above is solid).  A template parameter so that
+// the reference path carries no per-quad test for the other two.
+template <bool PACKED, int kEmitSplit, int TYPES>
 __global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
 {
@@ -564,6 +568,15 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         s.lut[i] = v;
     }
     if (tid >= 96 && tid < 128) s.nz_coarse[tid - 96] = 0;        // entries past the last non-empty row are never used
+    if (tid >= 128 && tid < 192) {
+        // k-th set bit of the 6-bit face pattern fb, for all k at once: faces LEFT..UP in emission order
+        const uint32_t fb = tid - 128u;
+        uint32_t packed = 0, k = 0;
+#pragma unroll
+        for (uint32_t g = 0; g < 6; ++g)
+            if ((fb >> g) & 1u) packed |= g << (3u * k++);
+        s.face_sel[fb] = packed;
+    }
     if (tid < 96) {
         // coordinate.rs:60-65 + chunk.rs:66,68,76 + quad.rs:42: (chunk*32 + local) as f32
         const uint32_t axis = tid >> 5, v = tid & 31u;
@@ -615,6 +628,12 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     uint32_t *out32 = reinterpret_cast<uint32_t *>(a.out);
     const unsigned long long chunk_word0 = (a.offsets[m] - a.quad_base) * 17ull;   // first word of this chunk
     const bool out_aligned = (reinterpret_cast<unsigned long long>(out32) & 15ull) == 0;
+    // A 32-quad tile is 544 words = 136 x 16 bytes, so every tile of the chunk starts at the same offset inside a
+    // 16-byte line as the chunk itself: the alignment arithmetic is per chunk, and tile addresses are 32-bit offsets
+    // from the chunk's base.  stage word i <-> chunk word (tile * 544 - lead + i).
+    uint32_t *const out_chunk = out32 + chunk_word0;
+    const uint32_t lead = (uint32_t)(chunk_word0 & 3ull);
+    const uint32_t body0 = lead ? 4u : 0u;                  // first 16-byte aligned stage word at or after `lead`
     const uint32_t *typ_rows = a.typ ? a.typ + (size_t)m * VX_ROWS : nullptr;
     const uint32_t n_tiles = (count + 31u) >> 5;
     uint32_t it = 0;
@@ -629,8 +648,6 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
 
         const uint32_t q0 = tile << 5;
         const uint32_t nq = min(32u, count - q0);
-        const unsigned long long G = chunk_word0 + (unsigned long long)q0 * 17ull;
-        const uint32_t lead = (uint32_t)(G & 3ull);            // stage word i <-> global word G - lead + i
         // Row of every quad of the tile, cooperatively: idx0 = the non-empty row holding q0 (two
         // 32-way ballots over nz_base), then each later row start inside the tile sets one bit.
         const uint32_t c_probe = s.nz_coarse[lane];
@@ -659,17 +676,13 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
                 if (c <= k) { x += step; before = c; }
             }
             k -= before;
-            // face: the k-th set face bit of cube x, in LEFT,RIGHT,BACK,FRONT,DOWN,UP order
-            uint32_t face = 0, seen = 0;
+            // face: the k-th set face bit of cube x, in LEFT,RIGHT,BACK,FRONT,DOWN,UP order (table look-up)
+            uint32_t fb = 0;
 #pragma unroll
-            for (uint32_t g = 0; g < 6; ++g) {
-                const uint32_t bit = (f.m[g] >> x) & 1u;
-                if (bit && seen == k) face = g;
-                seen += bit;
-            }
-            // block type: the caller's DIRT plane, or (extension) DIRT where the voxel above is solid
-            const uint32_t type = typ_rows ? ((__ldg(typ_rows + r) >> x) & 1u)
-                                           : (a.dirt_rule ? ((s.c.occ[32 + r + 32] >> x) & 1u) : 0u);
+            for (uint32_t g = 0; g < 6; ++g) fb |= ((f.m[g] >> x) & 1u) << g;
+            const uint32_t face = (s.face_sel[fb] >> (3u * k)) & 7u;
+            const uint32_t type = TYPES == 1 ? ((__ldg(typ_rows + r) >> x) & 1u)
+                                : TYPES == 2 ? ((s.c.occ[32 + r + 32] >> x) & 1u) : 0u;
             if (PACKED) {
                 // 128 B per warp, coalesced
                 out32[(a.offsets[m] - a.quad_base) + q] = (r << 5) | x | (face << 15) | (type << 18);
@@ -691,23 +704,21 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
         if (PACKED) continue;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
         __syncwarp();
-        const uint32_t nwords = nq * 17u;
-        // 16-B aligned body [Ga, Gb) leaves as one bulk store; the <= 3-word head and tail (or
-        // everything, if the caller's buffer is not 16-B aligned) as scalar stores
-        unsigned long long Ga = (G + 3ull) & ~3ull, Gb = (G + nwords) & ~3ull;
-        if (!out_aligned || Gb <= Ga) Ga = Gb = G;
-        if (lane == 0 && Gb > Ga)
-            bulk_store(out32 + Ga, stg + (uint32_t)(Ga - G) + lead, (uint32_t)(Gb - Ga) * 4u);
-        const uint32_t head = (uint32_t)(Ga - G), tail0 = (uint32_t)(Gb - G);
-        if (Gb > Ga) {
+        // Stage words [lead, lead + nwords) hold the tile.  The 16-byte aligned body [body0, body1) leaves as one bulk
+        // store; the <= 3-word head and tail (or everything, if the caller's buffer is not 16-byte aligned) as
+        // scalar stores.
+        const uint32_t end = lead + nq * 17u, body1 = end & ~3u;
+        uint32_t *const gdst = out_chunk + ((ptrdiff_t)(tile * 544u) - (ptrdiff_t)lead);   // stage word i -> gdst[i]
+        if (out_aligned && body1 > body0) {
+            if (lane == 0) bulk_store(gdst + body0, stg + body0, (body1 - body0) * 4u);
             // at most 3 head + 3 tail words: one predicated store
-            const uint32_t n_edge = head + (nwords - tail0);
+            const uint32_t head = body0 - lead, n_edge = head + (end - body1);
             if (lane < n_edge) {
-                const uint32_t wi = (lane < head) ? lane : tail0 + (lane - head);
-                out32[G + wi] = stg[lead + wi];
+                const uint32_t wi = (lane < head) ? lead + lane : body1 + (lane - head);
+                gdst[wi] = stg[wi];
             }
         } else {
-            for (uint32_t i = lane; i < nwords; i += 32u) out32[G + i] = stg[lead + i];
+            for (uint32_t i = lead + lane; i < end; i += 32u) gdst[i] = stg[i];
         }
     }
     if (!PACKED && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
@@ -777,20 +788,24 @@ cudaError_t vx_launch_mesh_count(const vx_mesh_args &a, cudaStream_t s, vx_count
     return cudaGetLastError();
 }
 
+template <bool PACKED, int SPLIT>
+static void launch_emit_types(const vx_mesh_args &a, uint32_t len, size_t smem, cudaStream_t s)
+{
+    if (a.typ) vx_mesh_emit_kernel<PACKED, SPLIT, 1><<<len * SPLIT, kEmitThreads, smem, s>>>(a);
+    else if (a.dirt_rule) vx_mesh_emit_kernel<PACKED, SPLIT, 2><<<len * SPLIT, kEmitThreads, smem, s>>>(a);
+    else vx_mesh_emit_kernel<PACKED, SPLIT, 0><<<len * SPLIT, kEmitThreads, smem, s>>>(a);
+}
+
 cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_t s, vx_counter *launches)
 {
     if (len == 0) return cudaSuccess;
     static_assert(sizeof(EmitSmem) <= 64 * 1024, "emit kernel shared memory budget");
     if (len <= kEmitSmallList) {
-        if (a.packed)
-            vx_mesh_emit_kernel<true, kEmitSplitSmall><<<len * kEmitSplitSmall, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
-        else
-            vx_mesh_emit_kernel<false, kEmitSplitSmall><<<len * kEmitSplitSmall, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+        if (a.packed) launch_emit_types<true, kEmitSplitSmall>(a, len, offsetof(EmitSmem, stage), s);
+        else launch_emit_types<false, kEmitSplitSmall>(a, len, sizeof(EmitSmem), s);
     } else {
-        if (a.packed)
-            vx_mesh_emit_kernel<true, 1><<<len, kEmitThreads, offsetof(EmitSmem, stage), s>>>(a);
-        else
-            vx_mesh_emit_kernel<false, 1><<<len, kEmitThreads, sizeof(EmitSmem), s>>>(a);
+        if (a.packed) launch_emit_types<true, 1>(a, len, offsetof(EmitSmem, stage), s);
+        else launch_emit_types<false, 1>(a, len, sizeof(EmitSmem), s);
     }
     if (launches) launches->fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
@@ -798,13 +813,21 @@ cudaError_t vx_launch_mesh_emit(const vx_mesh_args &a, uint32_t len, cudaStream_
 
 // Per-device kernel attributes (dynamic shared memory above 48 KB); called by vx_create with
 // the device current.
+template <int SPLIT, int TYPES>
+static cudaError_t allow_emit_smem()
+{
+    return cudaFuncSetAttribute(vx_mesh_emit_kernel<false, SPLIT, TYPES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(EmitSmem));
+}
+
 cudaError_t vx_init_mesh_kernels()
 {
-    cudaError_t e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(EmitSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(vx_mesh_emit_kernel<false, kEmitSplitSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(EmitSmem));
+    cudaError_t e = allow_emit_smem<1, 0>();
+    if (e == cudaSuccess) e = allow_emit_smem<1, 1>();
+    if (e == cudaSuccess) e = allow_emit_smem<1, 2>();
+    if (e == cudaSuccess) e = allow_emit_smem<kEmitSplitSmall, 0>();
+    if (e == cudaSuccess) e = allow_emit_smem<kEmitSplitSmall, 1>();
+    if (e == cudaSuccess) e = allow_emit_smem<kEmitSplitSmall, 2>();
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(vx_resolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(2 * kSmallResolve * 4 + kSmallResolve * 12));

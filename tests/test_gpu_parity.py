@@ -899,3 +899,35 @@ def test_terrain_opts_off_is_the_reference_path(ctx):
                                offsets.ctypes.data, inst.ctypes.data, len(inst), C.addressof(total), blocks.ctypes.data)
     assert rc == 0 and total.value == a.total
     assert inst.tobytes() == a.instances.tobytes() and np.array_equal(blocks, a.blocks)
+
+
+def test_out_of_range_neighbour_index(ctx, vox, oracle):
+    """an nbr_idx entry >= n must not make the mesher read another allocation.  Host entry point:
+    VX_ERR_BAD_ARG before anything is enqueued; device entry point: treated as None, status bit 2 raised."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(9)
+    coords = _grid(0, 0, 2, 2)
+    n = len(coords)
+    blocks = rng.choice(np.array([0, 2], np.uint8), size=(n, 32768), p=[0.5, 0.5])
+    wiring = np.full((n, 4), -1, np.int32)
+    wiring[1, 0] = 0
+    bad = wiring.copy()
+    bad[2, 3] = n + 5
+    with pytest.raises(vox.VoxError) as e:
+        ctx.mesh(coords, blocks, nbr_idx=bad)
+    assert e.value.code == vox._lib.VX_ERR_BAD_ARG
+    good = ctx.mesh(coords, blocks, nbr_idx=wiring)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(v).to(dev) for k, v in dict(c=coords, b=blocks, w=bad).items()}
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_inst = torch.zeros((good.total + 8) * 17, dtype=torch.int32, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with vox.Context() as c2:
+        c2.mesh_device(d["c"].data_ptr(), n, d["b"].data_ptr(), d_counts.data_ptr(), d_off.data_ptr(), d_inst.data_ptr(),
+                       good.total + 8, nbr_idx_ptr=d["w"].data_ptr(), status_ptr=st.data_ptr(), stream=s.cuda_stream)
+        s.synchronize()
+    assert int(st.item()) & 4                                   # VX_ST_BAD_NBR
+    assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), good.counts)     # the bad entry meshed as None
+    assert d_inst[:good.total * 17].cpu().numpy().tobytes() == good.instances.tobytes()

@@ -931,3 +931,47 @@ def test_out_of_range_neighbour_index(ctx, vox, oracle):
     assert int(st.item()) & 4                                   # VX_ST_BAD_NBR
     assert np.array_equal(d_counts.cpu().numpy().astype(np.uint32), good.counts)     # the bad entry meshed as None
     assert d_inst[:good.total * 17].cpu().numpy().tobytes() == good.instances.tobytes()
+
+
+def test_frustum_single_frame_kernel(ctx, vox, oracle):
+    """One plane set per launch takes its own kernel (four chunks per thread group, 128-bit coordinate loads, one or
+    two groups per thread): ragged sizes around every granularity, NaN / zero / wrapping inputs, both outputs, and
+    misaligned device pointers (which must fall back to the general kernel) -- all equal to the oracle."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(23)
+    for n in (1, 3, 4, 5, 31, 32, 33, 127, 128, 129, 1000, 4099, 606208, 606211, 700003):
+        planes = rng.standard_normal((1, 6, 4)).astype(np.float32)
+        planes[:, :, 3] += 300.0
+        if n % 3 == 0:
+            planes[0, 4, 1] = np.nan              # NaN distance counts as inside (frustum_culling.rs:33)
+        coords = rng.integers(-60, 60, size=(n, 3)).astype(np.int32)
+        coords[0] = (1 << 26, 0, -(1 << 26))      # wrapping world coordinates
+        want = oracle.frustum_cull(planes, coords)
+        got = ctx.frustum_cull(planes, coords)
+        assert np.array_equal(got, want), n
+        bits = ctx.frustum_cull(planes, coords, bits=True)
+        assert np.array_equal(np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :n], want), n
+        assert bits.shape[1] == (n + 31) // 32
+    # device pointers that are not 16-byte (coords) / 4-byte (visible) aligned
+    dev = torch.device("cuda", 0)
+    n = 5001
+    coords = rng.integers(-60, 60, size=(n, 3)).astype(np.int32)
+    planes = rng.standard_normal((1, 6, 4)).astype(np.float32)
+    planes[:, :, 3] += 300.0
+    want = oracle.frustum_cull(planes, coords)[0]
+    d_p = torch.from_numpy(planes).to(dev)
+    raw_c = torch.zeros(3 * n + 8, dtype=torch.int32, device=dev)
+    raw_v = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    d_bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with vox.Context() as c2:
+        for c_off, v_off in ((0, 0), (1, 0), (0, 3), (3, 1)):
+            raw_c[c_off:c_off + 3 * n] = torch.from_numpy(coords.reshape(-1)).to(dev)
+            raw_v.zero_()
+            c2.frustum_cull_device(d_p.data_ptr(), 1, raw_c.data_ptr() + 4 * c_off, n, visible_ptr=raw_v.data_ptr() + v_off,
+                                   bits_ptr=d_bits.data_ptr(), stream=s.cuda_stream)
+            s.synchronize()
+            assert np.array_equal(raw_v[v_off:v_off + n].cpu().numpy(), want), (c_off, v_off)
+            assert int(raw_v[v_off + n:].sum().item()) == 0 and int(raw_v[:v_off].sum().item()) == 0
+            b = np.unpackbits(d_bits.cpu().numpy().view(np.uint8), bitorder="little")[:n]
+            assert np.array_equal(b, want)

@@ -17,6 +17,8 @@
 // x and z (simdnoise x and y, perlin_noise.rs:7-12) are invariant along the
 // walk, so their per-octave products and x+y sums are hoisted.
 // FP32 ALU + INT32 bound; no tensor cores (nothing here is a contraction).
+#include <cstdlib>
+
 #include "vx_common.cuh"
 #include "vx_noise.cuh"
 
@@ -348,17 +350,22 @@ __device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float 
     return my_word;
 }
 
-template <bool WANT_BLOCKS>
+// ZB = z blocks per CTA (a CTA owns 32 x 4 ZB x 32 voxels): one index box, one table build and one barrier pair serve
+// ZB times the voxels (the box grows by at most one lattice point along j), and a warp's 8 ZB steps average out the
+// 1 / 2 / 3-evaluation steps better before the final barrier.  Large batches use ZB = 4; short lists keep ZB = 1 so that
+// the grid still fills the machine (dispatch in vx_launch_fill).
+template <bool WANT_BLOCKS, int ZB>
 // 64 registers -> 4 CTAs (32 warps) per SM: measured 0.326 / 0.301 / 0.288 ms at 2 / 3 / 4 CTAs per SM
 __global__ void __launch_bounds__(256, 4)
 vx_fill_lattice_kernel(const vx_fill_args a)
 {
-    __shared__ __align__(8) uint8_t nib[32][4][8];        // [y][z & 3][x block] -> 4 occupancy bits
+    __shared__ __align__(8) uint8_t nib[ZB][32][4][8];    // [z block][y][z & 3][x block] -> 4 occupancy bits
     __shared__ __align__(16) unsigned char s_tab[3][VXL_TAB_BYTES];
     __shared__ float s_box[3][6];                         // per octave: min i, j, k, max i, j, k (exact integers)
     __shared__ float4 s_og[3];                            // per octave: box minimum and 2^23 + table address
     const uint32_t lane = threadIdx.x & 31u, xblk = threadIdx.x >> 5;
-    const uint32_t item = blockIdx.x >> 3, zblk = blockIdx.x & 7u;
+    constexpr uint32_t kGroups = 8u / ZB;                 // CTAs per chunk
+    const uint32_t item = blockIdx.x / kGroups, zgrp = blockIdx.x % kGroups;
     const int32_t cx = a.coords[3 * item + 0], cy = a.coords[3 * item + 1], cz = a.coords[3 * item + 2];
     const float ox = (float)(int32_t)((uint32_t)cx * 32u);
     const float oy = (float)(int32_t)((uint32_t)cz * 32u);
@@ -366,11 +373,11 @@ vx_fill_lattice_kernel(const vx_fill_args a)
     const float freq = a.p.freq, lac = a.p.lacunarity, gain = a.p.gain, scale = a.p.simplex_scale;
     const uint32_t seed = (uint32_t)a.p.seed;
 
-    // ---- index box of this CTA's 32 x 4 x 32 voxels, per octave: floor values at the 8 corners
+    // ---- index box of this CTA's 32 x 4 ZB x 32 voxels, per octave: floor values at the 8 corners
     if (threadIdx.x < 32u) {
         const uint32_t o = min(lane >> 3, 2u), c = lane & 7u;
         float fx = __fmul_rn(__fadd_rn(ox, (c & 1u) ? 31.0f : 0.0f), freq);
-        float fy = __fmul_rn(__fadd_rn(oy, (float)(zblk * 4u + ((c & 2u) ? 3u : 0u))), freq);
+        float fy = __fmul_rn(__fadd_rn(oy, (float)(zgrp * 4u * ZB + ((c & 2u) ? 4u * ZB - 1u : 0u))), freq);
         float fz = __fmul_rn(__fadd_rn(oz, (c & 4u) ? 31.0f : 0.0f), freq);
 #pragma unroll
         for (uint32_t q = 0; q < 2u; ++q)
@@ -401,10 +408,17 @@ vx_fill_lattice_kernel(const vx_fill_args a)
               vxl_axis_fits(s_box[o][2], s_box[o][5]);
     const uint32_t xx = lane & 3u, zz = (lane >> 2) & 3u, yy = lane >> 4;
     const float sx = __fadd_rn(ox, (float)(xblk * 4u + xx));
-    const float sy = __fadd_rn(oy, (float)(zblk * 4u + zz));
-    uint32_t my_word = 0;
     if (!fit) {
-        my_word = vx_brick_exact_steps(sx, sy, oz, yy, lane, freq, lac, gain, scale, seed);
+#pragma unroll 1
+        for (uint32_t zs = 0; zs < (uint32_t)ZB; ++zs) {
+            const float sy = __fadd_rn(oy, (float)((zgrp * ZB + zs) * 4u + zz));
+            const uint32_t my_word = vx_brick_exact_steps(sx, sy, oz, yy, lane, freq, lac, gain, scale, seed);
+            if (lane < 16u) {
+#pragma unroll
+                for (uint32_t p8 = 0; p8 < 8u; ++p8)
+                    nib[zs][2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
+            }
+        }
     } else {
         // ---- hash every lattice point of the three boxes once (+1 per axis for the far corners)
 #pragma unroll 1
@@ -421,7 +435,16 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             }
         }
         __syncthreads();
+        const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
+        // fused path: one product by (scale * amplitude) instead of the exact path's two roundings (covered by errm)
+        const float ka1 = __fmul_rn(scale, amp1), ka2 = __fmul_rn(scale, amp2);
+        const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
+        const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
 
+#pragma unroll 1
+      for (uint32_t zs = 0; zs < (uint32_t)ZB; ++zs) {
+        const float sy = __fadd_rn(oy, (float)((zgrp * ZB + zs) * 4u + zz));
+        uint32_t my_word = 0;
         // two voxels per thread: (y, y + 2) of one (x, z) column -> the x / z terms are broadcast pairs
         float2 hx[3], hy[3], hxy[3];
         {
@@ -434,11 +457,6 @@ vx_fill_lattice_kernel(const vx_fill_args a)
                 hxy[o] = VX2(__fadd_rn(fx, fy));
             }
         }
-        const float amp1 = __fmul_rn(1.0f, gain), amp2 = __fmul_rn(amp1, gain);
-        // fused path: one product by (scale * amplitude) instead of the exact path's two roundings (covered by errm)
-        const float ka1 = __fmul_rn(scale, amp1), ka2 = __fmul_rn(scale, amp2);
-        const float errm = a.err_margin;             // certified bound on |fused - exact| of u, u+t, r (x3 slack)
-        const float thr1 = a.thr1 + errm, thr2 = a.thr2 + errm;
 #pragma unroll 1
         for (uint32_t it = 0; it < 8u; ++it) {
             const float ya = __fadd_rn(oz, (float)(4u * it + yy)), yb = __fadd_rn(oz, (float)(4u * it + yy + 2u));
@@ -484,20 +502,22 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             if (lane == 2u * it) my_word = word_a;
             if (lane == 2u * it + 1u) my_word = word_b;
         }
-    }
-    if (lane < 16u) {
-        // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
+        if (lane < 16u) {
+            // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
 #pragma unroll
-        for (uint32_t p8 = 0; p8 < 8u; ++p8)
-            nib[2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
+            for (uint32_t p8 = 0; p8 < 8u; ++p8)
+                nib[zs][2u * lane + (p8 >> 2)][p8 & 3u][xblk] = (uint8_t)((my_word >> (4u * p8)) & 15u);
+        }
+      }
     }
     __syncthreads();
 
-    // 128 row words of this z block: row (y, zblk*4 + zz) = 8 nibbles, one per x block
-    const uint32_t t = threadIdx.x;
-    const uint32_t rr = t >> 1, half = t & 1u;                  // row 0..127, 16-voxel half
-    const uint32_t y = rr >> 2, zq = rr & 3u;
-    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[y][zq][0]);
+    // 128 ZB row words of this CTA: row (y, z) = 8 nibbles, one per x block
+#pragma unroll
+    for (uint32_t q = threadIdx.x; q < 256u * ZB; q += 256u) {
+    const uint32_t rr = q >> 1, half = q & 1u;                  // row 0 .. 128 ZB - 1, 16-voxel half
+    const uint32_t zs = rr >> 7, y = (rr >> 2) & 31u, zq = rr & 3u, zblk = zgrp * ZB + zs;
+    const uint2 nb = *reinterpret_cast<const uint2 *>(&nib[zs][y][zq][0]);
     const uint32_t lo = (nb.x & 0x0f0f0f0fu), hi = (nb.y & 0x0f0f0f0fu);
     const uint32_t plo = (lo | (lo >> 4)) & 0x00ff00ffu, phi = (hi | (hi >> 4)) & 0x00ff00ffu;
     const uint32_t w16lo = (plo | (plo >> 8)) & 0xffffu, w16hi = (phi | (phi >> 8)) & 0xffffu;
@@ -512,6 +532,7 @@ vx_fill_lattice_kernel(const vx_fill_args a)
         v.w = (((air16 >> 12) & 15u) * 0x00204081u & 0x01010101u) << 1;
         *reinterpret_cast<uint4 *>(a.blocks + (size_t)item * VX_VOXELS + (size_t)y * 1024u +
                                    (zblk * 4u + zq) * 32u + half * 16u) = v;
+    }
     }
 }
 
@@ -579,8 +600,19 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
         // not fit (f32 spacing at huge coordinates) take their in-kernel exact path
         const float f0 = fabsf(a.p.freq), f1 = f0 * fabsf(a.p.lacunarity), f2 = f1 * fabsf(a.p.lacunarity);
         if (fmaxf(f0, fmaxf(f1, f2)) <= 0.1f) {
-            if (a.blocks) vx_fill_lattice_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
-            else vx_fill_lattice_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);
+            // z blocks per CTA: as many as still leave >= ~8 waves of CTAs (592 resident on 148 SMs)
+            static const int zb_env = [] { const char *e = getenv("VX_FILL_ZB"); return e ? atoi(e) : 0; }();   // A/B aid
+            const int zb = zb_env ? zb_env : (n_items >= 4096u ? 4 : (n_items >= 1024u ? 2 : 1));
+            if (zb == 4) {
+                if (a.blocks) vx_fill_lattice_kernel<true, 4><<<n_items * 2u, 256, 0, s>>>(b);
+                else vx_fill_lattice_kernel<false, 4><<<n_items * 2u, 256, 0, s>>>(b);
+            } else if (zb == 2) {
+                if (a.blocks) vx_fill_lattice_kernel<true, 2><<<n_items * 4u, 256, 0, s>>>(b);
+                else vx_fill_lattice_kernel<false, 2><<<n_items * 4u, 256, 0, s>>>(b);
+            } else {
+                if (a.blocks) vx_fill_lattice_kernel<true, 1><<<n_items * 8u, 256, 0, s>>>(b);
+                else vx_fill_lattice_kernel<false, 1><<<n_items * 8u, 256, 0, s>>>(b);
+            }
         } else {
             if (a.blocks) vx_fill_brick2_kernel<true><<<n_items * 8u, 256, 0, s>>>(b);
             else vx_fill_brick2_kernel<false><<<n_items * 8u, 256, 0, s>>>(b);

@@ -933,6 +933,57 @@ def test_out_of_range_neighbour_index(ctx, vox, oracle):
     assert d_inst[:good.total * 17].cpu().numpy().tobytes() == good.instances.tobytes()
 
 
+def test_frustum_extreme_corner_classes(ctx, vox, oracle):
+    """The frustum kernels decide most chunks from two corners per plane (kernels_frustum.cu: the corners the
+    coefficient signs pick) and run the reference's corner-by-corner test only on chunks that straddle a plane, or
+    on every chunk when a coefficient is NaN, infinite or above 2^90.  Every sign class, signed zeros, denormal and
+    huge coefficients, the 2^90 boundary from both sides, plane sets that cut through the grid so that whole rows
+    straddle, and the wrapping limit of the coordinates -- one frame per launch and many -- equal the oracle."""
+    from tools.bench_configs import camera_planes
+    rng = np.random.default_rng(41)
+    lim = np.float32(2.0 ** 90)
+    sets = []
+    for k in range(8):                                      # the eight sign classes on every plane slot
+        pl = np.abs(rng.standard_normal((6, 4))).astype(np.float32) + np.float32(0.05)
+        pl[:, 0] *= -1 if k & 1 else 1
+        pl[:, 1] *= -1 if k & 2 else 1
+        pl[:, 2] *= -1 if k & 4 else 1
+        pl[:, 3] = rng.uniform(-400, 1500, 6).astype(np.float32)
+        sets.append(pl)
+    for scale in (1e-42, 1e-30, 1e20, 2.0 ** 89):
+        pl = np.clip((rng.standard_normal((6, 4)) * scale).astype(np.float32), -lim, lim)
+        pl[:, 3] = (rng.standard_normal(6) * scale * 900).astype(np.float32).clip(-lim, lim)
+        sets.append(pl)
+    for special in (-0.0, 0.0, lim, -lim, np.nextafter(lim, np.float32(np.inf)), 3e38, np.inf, -np.inf, np.nan):
+        pl = rng.standard_normal((6, 4)).astype(np.float32)
+        pl[:, 3] += 600.0
+        pl[rng.integers(6), rng.integers(3)] = special
+        sets.append(pl)
+    pl = rng.standard_normal((6, 4)).astype(np.float32)
+    pl[:, 3] += 600.0
+    pl[2, 3] = np.nan                                        # NaN in d: that plane never rejects (:33)
+    sets.append(pl)
+    sets.extend(camera_planes(9, vox).reshape(9, 6, 4))      # thin bands of straddlers along the side planes
+    planes = np.stack(sets).astype(np.float32)
+    g = np.arange(-45, 45, dtype=np.int32)
+    z, x = np.meshgrid(g, g, indexing="ij")
+    grid = np.stack([x.reshape(-1), rng.integers(-1, 2, x.size).astype(np.int32), z.reshape(-1)], 1)
+    far = rng.integers(-(1 << 26), 1 << 26, size=(515, 3)).astype(np.int32)
+    far[:3] = [((1 << 26) - 1, 0, -(1 << 26)), (1 << 26, -1, (1 << 26) + 5), (-(1 << 26) - 1, 1, 0)]
+    coords = np.ascontiguousarray(np.concatenate([grid, far]).astype(np.int32))
+    want = oracle.frustum_cull(planes, coords)
+    assert 0 < want.sum() < want.size
+    got = ctx.frustum_cull(planes, coords)                                      # general kernel, all frames
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+    bits = ctx.frustum_cull(planes, coords, bits=True)
+    assert np.array_equal(np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :len(coords)], want)
+    for f in range(len(planes)):                                                # single-frame kernel
+        one = ctx.frustum_cull(planes[f:f + 1], coords)
+        assert np.array_equal(one[0], want[f]), (f, planes[f])
+        b1 = ctx.frustum_cull(planes[f:f + 1], coords, bits=True)
+        assert np.array_equal(np.unpackbits(b1.view(np.uint8), axis=1, bitorder="little")[0, :len(coords)], want[f]), f
+
+
 def test_frustum_single_frame_kernel(ctx, vox, oracle):
     """One plane set per launch takes its own kernel (four chunks per thread group, 128-bit coordinate loads, one or
     two groups per thread): ragged sizes around every granularity, NaN / zero / wrapping inputs, both outputs, and

@@ -33,18 +33,6 @@ __device__ __forceinline__ void plane_dist(const float4 pl, float x0, float x1, 
     const float2 t11 = __fadd2_rn(__fadd2_rn(s1, make_float2(cz1, cz1)), d);      // (x, y1, z1)
     t[0] = t00; t[1] = t01; t[2] = t10; t[3] = t11;
 }
-// two planes per step: min(min(m, a), b) is one three-input FMNMX3 on sm_100.  fminf ignores a NaN operand, which
-// is the reference's behaviour (a NaN distance never rejects, :33)
-__device__ __forceinline__ void plane_pair_step(const float4 pa, const float4 pb, float x0, float x1, float y0, float y1,
-                                                float z0, float z1, float2 (&m)[4])
-{
-    float2 ta[4], tb[4];
-    plane_dist(pa, x0, x1, y0, y1, z0, z1, ta);
-    plane_dist(pb, x0, x1, y0, y1, z0, z1, tb);
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        m[c] = make_float2(fminf(fminf(m[c].x, ta[c].x), tb[c].x), fminf(fminf(m[c].y, ta[c].y), tb[c].y));
-}
 __device__ __forceinline__ float best_corner(const float2 (&m)[4])
 {
     return fmaxf(fmaxf(fmaxf(m[0].x, m[0].y), fmaxf(m[1].x, m[1].y)), fmaxf(fmaxf(m[2].x, m[2].y), fmaxf(m[3].x, m[3].y)));
@@ -52,7 +40,152 @@ __device__ __forceinline__ float best_corner(const float2 (&m)[4])
 
 constexpr int kThreads = 256;
 constexpr int kFramesPerCta = 64;
+// chunk AABBs a lane tests together: the per-plane bookkeeping (plane load, class dispatch, loop) is paid once for all
+#ifndef VX_FR_FRAME_BOXES
+#define VX_FR_FRAME_BOXES 4
+#endif
+#ifndef VX_FR_ONE_MERGE
+#define VX_FR_ONE_MERGE 0
+#endif
+#ifndef VX_FR_PLANE_UNROLL
+#define VX_FR_PLANE_UNROLL 1
+#endif
+constexpr int kFrameBoxes = VX_FR_FRAME_BOXES;       // general kernel
+constexpr int kPlaneUnroll = VX_FR_PLANE_UNROLL;     // planes per iteration of the class-dispatch loop
 
+// ---------------------------------------------------------------------------
+// Extreme-corner classification.  With finite coefficients the distance
+//   dist(x, y, z) = fl(fl(fl(fl(a*x) + fl(b*y)) + fl(c*z)) + d)            (frustum_culling.rs:29-32)
+// is a monotone function of each coordinate: IEEE round-to-nearest is monotone, so x <= x' gives fl(a*x) <= fl(a*x')
+// for a >= 0 (the reverse for a < 0), and p <= p' gives fl(p + q) <= fl(p' + q).  Over the eight corners of an AABB
+// the smallest distance to a plane is therefore the one at the corner chosen by the coefficient signs (x0 where
+// a >= 0, x1 where a < 0, ...: the "n corner") and the largest the one at the opposite ("p") corner -- of the very
+// same rounded expression the reference evaluates, not of its real-number idealisation.  Hence
+//   * some plane has dist(p corner) < 0    =>  that plane rejects all eight corners        =>  contains() = false,
+//   * no plane has dist(n corner) < 0      =>  every corner is inside every plane           =>  contains() = true,
+//   * exactly one plane k has dist(n corner) < 0 (and dist(p corner) >= 0): every corner is inside the other five
+//     planes, and the p corner of plane k is a corner of the AABB that is inside plane k too  =>  contains() = true,
+// and only an AABB that straddles two or more planes (the edges and the apex of the frustum) needs the reference's
+// corner-by-corner test (:27-38), which it then gets unchanged.  Two corners per plane instead of eight: 6 products,
+// 3 packed additions on the (n, p) pair, one minimum and one sign count.  (A distance of -0 is counted as a
+// straddle although it is not < 0: that only sends the chunk to the corner test more often than needed.)
+// The argument needs sums free of NaN and of inf - inf: coordinates are at most 2^31 in magnitude, so coefficients
+// up to 2^90 keep every product and partial sum finite (< 2^124); a plane set with a larger, infinite or NaN
+// coefficient (plane_class bit 3) takes the corner-by-corner test for every chunk.
+// ---------------------------------------------------------------------------
+template <int C> struct Boxes { float x0[C], x1[C], y0[C], y1[C], z0[C], z1[C]; };
+
+__device__ __forceinline__ uint32_t plane_class(const float4 pl)
+{
+    const float lim = 1.2379400392853803e27f;      // 2^90
+    const bool ok = fabsf(pl.x) <= lim && fabsf(pl.y) <= lim && fabsf(pl.z) <= lim && fabsf(pl.w) <= lim;   // false for NaN
+    return (pl.x < 0.0f ? 1u : 0u) | (pl.y < 0.0f ? 2u : 0u) | (pl.z < 0.0f ? 4u : 0u) | (ok ? 0u : 8u);
+}
+
+// pm[c] = running minimum over the planes of the distance at the p corner, ns[c] = number of planes whose distance
+// at the n corner has its sign bit set; K = sign class of the plane
+template <uint32_t K, int C>
+__device__ __forceinline__ void extreme_step(const float4 pl, const Boxes<C> &b, float (&pm)[C], uint32_t (&ns)[C])
+{
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float nx = (K & 1u) ? b.x1[c] : b.x0[c], px = (K & 1u) ? b.x0[c] : b.x1[c];
+        const float ny = (K & 2u) ? b.y1[c] : b.y0[c], py = (K & 2u) ? b.y0[c] : b.y1[c];
+        const float nz = (K & 4u) ? b.z1[c] : b.z0[c], pz = (K & 4u) ? b.z0[c] : b.z1[c];
+        // scalar products (see plane_dist), packed sums in the reference's association
+        float2 s = __fadd2_rn(make_float2(__fmul_rn(pl.x, nx), __fmul_rn(pl.x, px)),
+                              make_float2(__fmul_rn(pl.y, ny), __fmul_rn(pl.y, py)));
+        s = __fadd2_rn(s, make_float2(__fmul_rn(pl.z, nz), __fmul_rn(pl.z, pz)));
+        s = __fadd2_rn(s, make_float2(pl.w, pl.w));
+        pm[c] = fminf(pm[c], s.y);
+        ns[c] += __float_as_uint(s.x) >> 31;
+    }
+}
+
+// the reference's test of one AABB, corner by corner (order independent: plane by plane here).  Only chunks that
+// straddle a plane come here, so it is a rolled loop that stays small in code and registers.
+__device__ __forceinline__ bool corner_test(const float4 *pl, float x0, float x1, float y0, float y1, float z0, float z1)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float2 m[4] = {make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf)};
+#pragma unroll 1
+    for (uint32_t p = 0; p < 6; ++p) {
+        float2 t[4];
+        plane_dist(pl[p], x0, x1, y0, y1, z0, z1, t);
+        // fminf ignores a NaN operand, which is the reference's behaviour (a NaN distance never rejects, :33)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m[c] = make_float2(fminf(m[c].x, t[c].x), fminf(m[c].y, t[c].y));
+    }
+    return !(best_corner(m) < 0.0f);
+}
+
+// Visibility bits of a lane's C chunks against one plane set.  pl: six planes (shared memory), cls: their
+// classes, four bits per plane.  Must be called by the whole warp (planes are skipped once every lane is decided).
+template <int C>
+__device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, const Boxes<C> &b, uint32_t live)
+{
+    uint32_t vis = 0, todo = live;
+    if (!(cls & 0x888888u)) {
+        const float inf = __int_as_float(0x7f800000);
+        float pm[C];
+        uint32_t ns[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { pm[c] = inf; ns[c] = 0; }
+#pragma unroll(kPlaneUnroll)
+        for (uint32_t p = 0; p < 6; ++p) {
+            const float4 q = pl[p];
+            switch ((cls >> (4u * p)) & 7u) {                   // warp-uniform
+            case 0: extreme_step<0>(q, b, pm, ns); break;
+            case 1: extreme_step<1>(q, b, pm, ns); break;
+            case 2: extreme_step<2>(q, b, pm, ns); break;
+            case 3: extreme_step<3>(q, b, pm, ns); break;
+            case 4: extreme_step<4>(q, b, pm, ns); break;
+            case 5: extreme_step<5>(q, b, pm, ns); break;
+            case 6: extreme_step<6>(q, b, pm, ns); break;
+            default: extreme_step<7>(q, b, pm, ns); break;
+            }
+            if (p == 1 || p == 3) {
+                bool open = false;
+#pragma unroll
+                for (int c = 0; c < C; ++c) open |= ((live >> c) & 1u) && !(pm[c] < 0.0f);
+                if (!__any_sync(VX_FULL, open)) return 0;        // every chunk of the warp is rejected already
+            }
+        }
+        todo = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (((live >> c) & 1u) && !(pm[c] < 0.0f)) {
+                if (ns[c] <= 1u) vis |= 1u << c;
+                else todo |= 1u << c;                             // straddles two planes or more
+            }
+        }
+    }
+    while (todo) {
+        const uint32_t c = __ffs(todo) - 1;
+        todo &= todo - 1;
+        float x0 = b.x0[0], x1 = b.x1[0], y0 = b.y0[0], y1 = b.y1[0], z0 = b.z0[0], z1 = b.z1[0];
+#pragma unroll
+        for (int k = 1; k < C; ++k)
+            if (c == (uint32_t)k) { x0 = b.x0[k]; x1 = b.x1[k]; y0 = b.y0[k]; y1 = b.y1[k]; z0 = b.z0[k]; z1 = b.z1[k]; }
+        vis |= (corner_test(pl, x0, x1, y0, y1, z0, z1) ? 1u : 0u) << c;
+    }
+    return vis;
+}
+
+// coordinate.rs:53-58: (chunk * 32) as f32 (wrapping i32 product); frustum_culling.rs:19-26: the far corners are p + 32
+template <int C>
+__device__ __forceinline__ void set_box(Boxes<C> &b, int c, int32_t cx, int32_t cy, int32_t cz)
+{
+    b.x0[c] = (float)(int32_t)((uint32_t)cx * 32u);
+    b.y0[c] = (float)(int32_t)((uint32_t)cy * 32u);
+    b.z0[c] = (float)(int32_t)((uint32_t)cz * 32u);
+    b.x1[c] = __fadd_rn(b.x0[c], 32.0f);
+    b.y1[c] = __fadd_rn(b.y0[c], 32.0f);
+    b.z1[c] = __fadd_rn(b.z0[c], 32.0f);
+}
+
+// n chunks x up to kFramesPerCta plane sets per CTA.  A warp covers 32 * kFrameBoxes consecutive chunks, lane l the
+// chunks base + 32 k + l, so every store of a frame is a coalesced row and a ballot is one word of the bit output.
 template <bool WANT_BYTES, bool WANT_BITS>
 __global__ void __launch_bounds__(kThreads)
 vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
@@ -60,74 +193,58 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
                   uint8_t *__restrict__ visible, uint32_t *__restrict__ bits, uint32_t n_words)
 {
     __shared__ float4 s_pl[kFramesPerCta * 6];
+    __shared__ uint32_t s_cls[kFramesPerCta];
     const uint32_t f0 = blockIdx.y * kFramesPerCta;
     const uint32_t nf = min((uint32_t)kFramesPerCta, n_frames - f0);
-    for (uint32_t i = threadIdx.x; i < nf * 6; i += kThreads)
-        s_pl[i] = __ldg(reinterpret_cast<const float4 *>(planes) + (size_t)f0 * 6 + i);
+    const float4 *gp = reinterpret_cast<const float4 *>(planes) + (size_t)f0 * 6;
+    for (uint32_t i = threadIdx.x; i < nf * 6; i += kThreads) s_pl[i] = __ldg(gp + i);
+    if (threadIdx.x < nf) {
+        uint32_t cls = 0;
+#pragma unroll
+        for (uint32_t p = 0; p < 6; ++p) cls |= plane_class(__ldg(gp + threadIdx.x * 6 + p)) << (4u * p);
+        s_cls[threadIdx.x] = cls;
+    }
     __syncthreads();
 
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    const bool live = i < n;
-    // coordinate.rs:53-58: (chunk * 32) as f32 (wrapping i32 product);
-    // frustum_culling.rs:19-26: the far corners are p + 32.
-    float x0 = 0.f, y0 = 0.f, z0 = 0.f;
-    if (live) {
-        x0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 0) * 32u);
-        y0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 1) * 32u);
-        z0 = (float)(int32_t)((uint32_t)__ldg(coords + 3 * (size_t)i + 2) * 32u);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wbase = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * (32u * kFrameBoxes);
+    if (wbase >= n) return;
+    Boxes<kFrameBoxes> b;
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < kFrameBoxes; ++k) {
+        const uint32_t i = wbase + 32u * k + lane;
+        int32_t cx = 0, cy = 0, cz = 0;
+        if (i < n) {
+            cx = __ldg(coords + 3 * (size_t)i + 0);
+            cy = __ldg(coords + 3 * (size_t)i + 1);
+            cz = __ldg(coords + 3 * (size_t)i + 2);
+            live |= 1u << k;
+        }
+        set_box(b, k, cx, cy, cz);
     }
-    const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
 
     for (uint32_t f = 0; f < nf; ++f) {
-        // Per corner, the minimum over the planes of its distance: the corner is inside all six
-        // planes iff that minimum is not < 0.  fminf ignores a NaN operand, which is the
-        // reference's behaviour (a NaN distance never rejects, frustum_culling.rs:33).
-        const float inf = __int_as_float(0x7f800000);
-        float2 m[4] = {make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf)};
-        bool dead = false;
+        const uint32_t vis = frame_test(s_pl + f * 6, s_cls[f], b, live);
+        uint32_t mine = 0;
 #pragma unroll
-        for (uint32_t p = 1; p < 6; p += 2) {
-            plane_pair_step(s_pl[f * 6 + p - 1], s_pl[f * 6 + p], x0, x1, y0, y1, z0, z1, m);
-            if (p == 1 || p == 3) {
-                // the result is a pure function, so the remaining planes can be skipped once no
-                // lane of the warp has a live corner
-                if (!__any_sync(VX_FULL, live && !(best_corner(m) < 0.0f))) {
-                    dead = true;
-                    break;
-                }
-            }
+        for (int k = 0; k < kFrameBoxes; ++k) {
+            const uint32_t word = __ballot_sync(VX_FULL, (vis >> k) & 1u);
+            if (lane == (uint32_t)k) mine = word;
+            if (WANT_BYTES && ((live >> k) & 1u)) visible[(size_t)(f0 + f) * n + wbase + 32u * k + lane] = (vis >> k) & 1u;
         }
-        const bool vis = live && !dead && !(best_corner(m) < 0.0f);
-        const uint32_t word = __ballot_sync(VX_FULL, vis);
-        if (WANT_BYTES && live) visible[(size_t)(f0 + f) * n + i] = vis ? 1 : 0;
-        if (WANT_BITS && (threadIdx.x & 31) == 0 && live) bits[(size_t)(f0 + f) * n_words + (i >> 5)] = word;
+        if (WANT_BITS && lane < (uint32_t)kFrameBoxes && wbase + 32u * lane < n)
+            bits[(size_t)(f0 + f) * n_words + (wbase >> 5) + lane] = mine;
     }
 }
 
 // ---------------------------------------------------------------------------
 // One plane set per launch (the reference's own call shape: Frustum::contains against the current
 // camera, chunk_builder.rs:251 / world.rs:35, for every loaded chunk).  13 bytes per test, so the launch
-// is latency-bound: there is no shared-memory staging and no CTA barrier.  A thread owns FOUR consecutive
-// chunks whose 12 coordinates arrive as three 128-bit loads (a warp reads 1536 contiguous bytes); the
-// six planes are six uniform 128-bit loads issued beside them.  Same arithmetic and the same warp-level
-// plane skipping as the general kernel.
+// is latency-bound.  A thread owns groups of FOUR consecutive chunks whose 12 coordinates arrive as three
+// 128-bit loads (a warp reads 1536 contiguous bytes), all issued before anything else; warp 0 stages the
+// six planes and their classes in shared memory meanwhile.  Same classification as the general kernel.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ bool aabb_visible(const float4 (&pl)[6], int32_t cx, int32_t cy, int32_t cz, bool live)
-{
-    const float x0 = (float)(int32_t)((uint32_t)cx * 32u), y0 = (float)(int32_t)((uint32_t)cy * 32u),
-                z0 = (float)(int32_t)((uint32_t)cz * 32u);
-    const float x1 = __fadd_rn(x0, 32.0f), y1 = __fadd_rn(y0, 32.0f), z1 = __fadd_rn(z0, 32.0f);
-    const float inf = __int_as_float(0x7f800000);
-    float2 m[4] = {make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf), make_float2(inf, inf)};
-#pragma unroll
-    for (uint32_t p = 1; p < 6; p += 2) {
-        plane_pair_step(pl[p - 1], pl[p], x0, x1, y0, y1, z0, z1, m);
-        if (p == 1 || p == 3) {
-            if (!__any_sync(VX_FULL, live && !(best_corner(m) < 0.0f))) return false;
-        }
-    }
-    return live && !(best_corner(m) < 0.0f);
-}
 
 // G groups of four chunks per thread (group g of round r = r * threads + thread: every round is a
 // coalesced sweep).  The launcher picks G so that the whole grid is resident at once -- one wave, all
@@ -137,6 +254,8 @@ __global__ void __launch_bounds__(kThreads)
 vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restrict__ coords, uint32_t n,
                       uint8_t *__restrict__ visible, uint32_t *__restrict__ bits)
 {
+    __shared__ float4 s_pl[6];
+    __shared__ uint32_t s_cls;
     const uint32_t lane = threadIdx.x & 31u, stride = gridDim.x * kThreads;
     const uint32_t g0 = blockIdx.x * kThreads + threadIdx.x;     // first group of four chunks
     int32_t c[G][12];
@@ -153,29 +272,54 @@ vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restric
             for (uint32_t k = 0; k < 12; ++k) c[r][k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
         }
     }
-    float4 pl[6];
-#pragma unroll
-    for (uint32_t p = 0; p < 6; ++p) pl[p] = __ldg(reinterpret_cast<const float4 *>(planes) + p);
-#pragma unroll
-    for (int r = 0; r < G; ++r) {
-        const uint32_t g = g0 + r * stride, i0 = g * 4u;
-        if ((g & ~31u) * 4u >= n) break;                         // whole warp past the end (warp-uniform)
-        uint32_t nib = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k)
-            nib |= (aabb_visible(pl, c[r][3 * k], c[r][3 * k + 1], c[r][3 * k + 2], i0 + k < n) ? 1u : 0u) << k;
-        if (WANT_BYTES && i0 < n) {
-            const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-            if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;       // visible is 4-byte aligned (launcher)
-            else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+    if (threadIdx.x < 32u) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < 6u) {
+            q = __ldg(reinterpret_cast<const float4 *>(planes) + lane);
+            s_pl[lane] = q;
         }
-        if (WANT_BITS) {
-            // eight lanes hold one 32-chunk word
-            uint32_t v = nib << (4u * (lane & 7u));
-            v |= __shfl_xor_sync(VX_FULL, v, 1);
-            v |= __shfl_xor_sync(VX_FULL, v, 2);
-            v |= __shfl_xor_sync(VX_FULL, v, 4);
-            if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
+        const uint32_t cls = __reduce_or_sync(VX_FULL, lane < 6u ? plane_class(q) << (4u * lane) : 0u);
+        if (lane == 0u) s_cls = cls;
+    }
+    __syncthreads();
+    const uint32_t cls = s_cls;
+    // the G groups are classified together (VX_FR_ONE_MERGE) or one after the other
+    constexpr int kPass = VX_FR_ONE_MERGE ? 1 : G, kPer = VX_FR_ONE_MERGE ? G : 1;
+#pragma unroll
+    for (int pass = 0; pass < kPass; ++pass) {
+        if (((g0 + pass * kPer * stride) & ~31u) * 4u >= n) break;   // whole warp past the end (warp-uniform)
+        Boxes<4 * kPer> b;
+        uint32_t live = 0;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int r = pass * kPer + q;
+            const uint32_t i0 = (g0 + r * stride) * 4u;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                set_box(b, 4 * q + k, c[r][3 * k], c[r][3 * k + 1], c[r][3 * k + 2]);
+                live |= (i0 + k < n ? 1u : 0u) << (4 * q + k);
+            }
+        }
+        const uint32_t all = frame_test(s_pl, cls, b, live);
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int r = pass * kPer + q;
+            const uint32_t g = g0 + r * stride, i0 = g * 4u;
+            if (q > 0 && (g & ~31u) * 4u >= n) break;
+            const uint32_t nib = (all >> (4 * q)) & 15u;
+            if (WANT_BYTES && i0 < n) {
+                const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;   // visible is 4-byte aligned (launcher)
+                else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+            }
+            if (WANT_BITS) {
+                // eight lanes hold one 32-chunk word
+                uint32_t v = nib << (4u * (lane & 7u));
+                v |= __shfl_xor_sync(VX_FULL, v, 1);
+                v |= __shfl_xor_sync(VX_FULL, v, 2);
+                v |= __shfl_xor_sync(VX_FULL, v, 4);
+                if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
+            }
         }
     }
 }
@@ -203,7 +347,8 @@ cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int3
         if (launches) launches->fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     }
-    const dim3 grid((n + kThreads - 1) / kThreads, (n_frames + kFramesPerCta - 1) / kFramesPerCta);
+    const uint32_t per_cta = kThreads * kFrameBoxes;
+    const dim3 grid((n + per_cta - 1) / per_cta, (n_frames + kFramesPerCta - 1) / kFramesPerCta);
     const uint32_t n_words = (n + 31) / 32;
     if (visible && bits)
         vx_frustum_kernel<true, true><<<grid, kThreads, 0, s>>>(planes, n_frames, coords, n, visible, bits, n_words);

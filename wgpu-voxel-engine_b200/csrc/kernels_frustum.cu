@@ -44,14 +44,26 @@ constexpr int kFramesPerCta = 64;
 #ifndef VX_FR_FRAME_BOXES
 #define VX_FR_FRAME_BOXES 4
 #endif
-#ifndef VX_FR_ONE_MERGE
-#define VX_FR_ONE_MERGE 0
+#ifndef VX_FR_FRAME_UNROLL
+#define VX_FR_FRAME_UNROLL 6
 #endif
-#ifndef VX_FR_PLANE_UNROLL
-#define VX_FR_PLANE_UNROLL 1
+#ifndef VX_FR_ONE_UNROLL
+#define VX_FR_ONE_UNROLL 6
+#endif
+#ifndef VX_FR_ONE_THREADS
+#define VX_FR_ONE_THREADS 128
+#endif
+// evaluate the side planes (stored third and fourth, frustum_culling.rs:84) before near / far: the result does not
+// depend on the order, and in an open world the side planes reject the most chunks, so more warps are decided after
+// the first pair (378 -> 406 G tests/s on the camera sweep of BASELINE configs[4])
+#ifndef VX_FR_SIDES_FIRST
+#define VX_FR_SIDES_FIRST 1
 #endif
 constexpr int kFrameBoxes = VX_FR_FRAME_BOXES;       // general kernel
-constexpr int kPlaneUnroll = VX_FR_PLANE_UNROLL;     // planes per iteration of the class-dispatch loop
+// planes per iteration of the class-dispatch loop (both kernels measured fastest with the loop unrolled completely:
+// 334 -> 378 G tests/s at 1000 frames per launch, 5.7 -> 5.3 us for one frame)
+constexpr int kFrameUnroll = VX_FR_FRAME_UNROLL, kOneUnroll = VX_FR_ONE_UNROLL;
+constexpr int kOneThreads = VX_FR_ONE_THREADS;       // CTA size of the single-frame kernel
 
 // ---------------------------------------------------------------------------
 // Extreme-corner classification.  With finite coefficients the distance
@@ -121,7 +133,7 @@ __device__ __forceinline__ bool corner_test(const float4 *pl, float x0, float x1
 
 // Visibility bits of a lane's C chunks against one plane set.  pl: six planes (shared memory), cls: their
 // classes, four bits per plane.  Must be called by the whole warp (planes are skipped once every lane is decided).
-template <int C>
+template <int UNROLL, int C>
 __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, const Boxes<C> &b, uint32_t live)
 {
     uint32_t vis = 0, todo = live;
@@ -131,8 +143,10 @@ __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, c
         uint32_t ns[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { pm[c] = inf; ns[c] = 0; }
-#pragma unroll(kPlaneUnroll)
-        for (uint32_t p = 0; p < 6; ++p) {
+#pragma unroll(UNROLL)
+        for (uint32_t i = 0; i < 6; ++i) {
+            // the result does not depend on the order of the planes
+            const uint32_t p = (VX_FR_SIDES_FIRST && i < 4u) ? (i ^ 2u) : i;
             const float4 q = pl[p];
             switch ((cls >> (4u * p)) & 7u) {                   // warp-uniform
             case 0: extreme_step<0>(q, b, pm, ns); break;
@@ -144,7 +158,7 @@ __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, c
             case 6: extreme_step<6>(q, b, pm, ns); break;
             default: extreme_step<7>(q, b, pm, ns); break;
             }
-            if (p == 1 || p == 3) {
+            if (i == 1 || i == 3) {
                 bool open = false;
 #pragma unroll
                 for (int c = 0; c < C; ++c) open |= ((live >> c) & 1u) && !(pm[c] < 0.0f);
@@ -225,7 +239,7 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
     }
 
     for (uint32_t f = 0; f < nf; ++f) {
-        const uint32_t vis = frame_test(s_pl + f * 6, s_cls[f], b, live);
+        const uint32_t vis = frame_test<kFrameUnroll>(s_pl + f * 6, s_cls[f], b, live);
         uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < kFrameBoxes; ++k) {
@@ -241,36 +255,30 @@ vx_frustum_kernel(const float *__restrict__ planes, uint32_t n_frames,
 // ---------------------------------------------------------------------------
 // One plane set per launch (the reference's own call shape: Frustum::contains against the current
 // camera, chunk_builder.rs:251 / world.rs:35, for every loaded chunk).  13 bytes per test, so the launch
-// is latency-bound.  A thread owns groups of FOUR consecutive chunks whose 12 coordinates arrive as three
-// 128-bit loads (a warp reads 1536 contiguous bytes), all issued before anything else; warp 0 stages the
-// six planes and their classes in shared memory meanwhile.  Same classification as the general kernel.
+// is latency-bound.  A thread owns FOUR consecutive chunks whose 12 coordinates arrive as three 128-bit
+// loads (a warp reads 1536 contiguous bytes), issued before anything else; warp 0 stages the six planes
+// and their classes in shared memory meanwhile.  Same classification as the general kernel.  Measured on
+// 10^6 AABBs (tools/probes/frustum_ab.py): small CTAs and one group per thread (1.65 waves that balance
+// over the SMs) beat two groups per thread in one wave, 5.3 against 6.3 us.
 // ---------------------------------------------------------------------------
-
-// G groups of four chunks per thread (group g of round r = r * threads + thread: every round is a
-// coalesced sweep).  The launcher picks G so that the whole grid is resident at once -- one wave, all
-// loads of a thread issued up front.
-template <bool WANT_BYTES, bool WANT_BITS, int G>
-__global__ void __launch_bounds__(kThreads)
+template <bool WANT_BYTES, bool WANT_BITS>
+__global__ void __launch_bounds__(kOneThreads)
 vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restrict__ coords, uint32_t n,
                       uint8_t *__restrict__ visible, uint32_t *__restrict__ bits)
 {
     __shared__ float4 s_pl[6];
     __shared__ uint32_t s_cls;
-    const uint32_t lane = threadIdx.x & 31u, stride = gridDim.x * kThreads;
-    const uint32_t g0 = blockIdx.x * kThreads + threadIdx.x;     // first group of four chunks
-    int32_t c[G][12];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t g = blockIdx.x * kOneThreads + threadIdx.x, i0 = g * 4u;     // group of four chunks
+    int32_t c[12];
+    if (i0 + 4u <= n) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(coords) + (size_t)g * 3;
+        const uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y;
+        c[6] = b.z; c[7] = b.w; c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
+    } else {
 #pragma unroll
-    for (int r = 0; r < G; ++r) {
-        const uint32_t g = g0 + r * stride, i0 = g * 4u;
-        if (i0 + 4u <= n) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(coords) + (size_t)g * 3;
-            const uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
-            c[r][0] = a.x; c[r][1] = a.y; c[r][2] = a.z; c[r][3] = a.w; c[r][4] = b.x; c[r][5] = b.y;
-            c[r][6] = b.z; c[r][7] = b.w; c[r][8] = d.x; c[r][9] = d.y; c[r][10] = d.z; c[r][11] = d.w;
-        } else {
-#pragma unroll
-            for (uint32_t k = 0; k < 12; ++k) c[r][k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
-        }
+        for (uint32_t k = 0; k < 12; ++k) c[k] = (i0 + k / 3u < n) ? __ldg(coords + 3 * (size_t)i0 + k) : 0;
     }
     if (threadIdx.x < 32u) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -282,55 +290,36 @@ vx_frustum_one_kernel(const float *__restrict__ planes, const int32_t *__restric
         if (lane == 0u) s_cls = cls;
     }
     __syncthreads();
-    const uint32_t cls = s_cls;
-    // the G groups are classified together (VX_FR_ONE_MERGE) or one after the other
-    constexpr int kPass = VX_FR_ONE_MERGE ? 1 : G, kPer = VX_FR_ONE_MERGE ? G : 1;
+    if ((g & ~31u) * 4u >= n) return;                             // whole warp past the end (warp-uniform)
+    Boxes<4> b;
+    uint32_t live = 0;
 #pragma unroll
-    for (int pass = 0; pass < kPass; ++pass) {
-        if (((g0 + pass * kPer * stride) & ~31u) * 4u >= n) break;   // whole warp past the end (warp-uniform)
-        Boxes<4 * kPer> b;
-        uint32_t live = 0;
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int r = pass * kPer + q;
-            const uint32_t i0 = (g0 + r * stride) * 4u;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-                set_box(b, 4 * q + k, c[r][3 * k], c[r][3 * k + 1], c[r][3 * k + 2]);
-                live |= (i0 + k < n ? 1u : 0u) << (4 * q + k);
-            }
-        }
-        const uint32_t all = frame_test(s_pl, cls, b, live);
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int r = pass * kPer + q;
-            const uint32_t g = g0 + r * stride, i0 = g * 4u;
-            if (q > 0 && (g & ~31u) * 4u >= n) break;
-            const uint32_t nib = (all >> (4 * q)) & 15u;
-            if (WANT_BYTES && i0 < n) {
-                const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-                if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;   // visible is 4-byte aligned (launcher)
-                else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
-            }
-            if (WANT_BITS) {
-                // eight lanes hold one 32-chunk word
-                uint32_t v = nib << (4u * (lane & 7u));
-                v |= __shfl_xor_sync(VX_FULL, v, 1);
-                v |= __shfl_xor_sync(VX_FULL, v, 2);
-                v |= __shfl_xor_sync(VX_FULL, v, 4);
-                if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
-            }
-        }
+    for (uint32_t k = 0; k < 4; ++k) {
+        set_box(b, k, c[3 * k], c[3 * k + 1], c[3 * k + 2]);
+        live |= (i0 + k < n ? 1u : 0u) << k;
+    }
+    const uint32_t nib = frame_test<kOneUnroll>(s_pl, s_cls, b, live);
+    if (WANT_BYTES && i0 < n) {
+        const uint32_t w = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        if (i0 + 4u <= n) *reinterpret_cast<uint32_t *>(visible + i0) = w;       // visible is 4-byte aligned (launcher)
+        else for (uint32_t k = 0; i0 + k < n; ++k) visible[i0 + k] = (uint8_t)((nib >> k) & 1u);
+    }
+    if (WANT_BITS) {
+        // eight lanes hold one 32-chunk word
+        uint32_t v = nib << (4u * (lane & 7u));
+        v |= __shfl_xor_sync(VX_FULL, v, 1);
+        v |= __shfl_xor_sync(VX_FULL, v, 2);
+        v |= __shfl_xor_sync(VX_FULL, v, 4);
+        if ((lane & 7u) == 0u && i0 < n) bits[i0 >> 5] = v;
     }
 }
 
-template <int G>
 void launch_one(const float *planes, const int32_t *coords, uint32_t n, uint8_t *visible, uint32_t *bits, cudaStream_t s)
 {
-    const uint32_t groups = (n + 3u) / 4u, threads = (groups + G - 1) / G, g1 = (threads + kThreads - 1) / kThreads;
-    if (visible && bits) vx_frustum_one_kernel<true, true, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
-    else if (visible) vx_frustum_one_kernel<true, false, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
-    else vx_frustum_one_kernel<false, true, G><<<g1, kThreads, 0, s>>>(planes, coords, n, visible, bits);
+    const uint32_t groups = (n + 3u) / 4u, g1 = (groups + kOneThreads - 1) / kOneThreads;
+    if (visible && bits) vx_frustum_one_kernel<true, true><<<g1, kOneThreads, 0, s>>>(planes, coords, n, visible, bits);
+    else if (visible) vx_frustum_one_kernel<true, false><<<g1, kOneThreads, 0, s>>>(planes, coords, n, visible, bits);
+    else vx_frustum_one_kernel<false, true><<<g1, kOneThreads, 0, s>>>(planes, coords, n, visible, bits);
 }
 
 }  // namespace
@@ -341,9 +330,7 @@ cudaError_t vx_launch_frustum(const float *planes, uint32_t n_frames, const int3
     if (n == 0 || n_frames == 0) return cudaSuccess;
     if (n_frames == 1 && (reinterpret_cast<uintptr_t>(coords) & 15u) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15u) == 0 &&
         (!visible || (reinterpret_cast<uintptr_t>(visible) & 3u) == 0)) {
-        // one wave if possible: 148 SMs x 4 resident CTAs x 256 threads x 4 chunks = 606 k chunks with G = 1
-        if (n <= 148u * 4u * kThreads * 4u) launch_one<1>(planes, coords, n, visible, bits, s);
-        else launch_one<2>(planes, coords, n, visible, bits, s);
+        launch_one(planes, coords, n, visible, bits, s);
         if (launches) launches->fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     }

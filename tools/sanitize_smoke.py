@@ -26,9 +26,11 @@ g = np.indices((32, 32, 32)).sum(axis=0) & 1
 cb = np.where(g == 0, 0, 2).astype(np.uint8).reshape(-1)
 mm = ctx.mesh(coords[:2], np.stack([cb, r.blocks[0]]))                   # pack, count, emit (98304 quads)
 planes = np.random.default_rng(0).standard_normal((70, 6, 4)).astype(np.float32)
+planes[:40, :, 3] += 300.0            # frames decided by the extreme corners alone / frames full of straddling chunks
+planes[3, 2, 0] = np.nan              # a frame that takes the corner-by-corner test for every chunk
 v = ctx.frustum_cull(planes, coords)
 b = ctx.frustum_cull(planes, coords, bits=True)
-# single-frame kernel (G = 1; ragged tail) and its two-groups-per-thread form (> 606 k chunks)
+# single-frame kernel: ragged tail, and more than one wave of CTAs
 big = np.zeros((700003, 3), np.int32)
 big[:, 0] = np.arange(700003) % 997 - 400
 big[:, 2] = np.arange(700003) // 997 - 300

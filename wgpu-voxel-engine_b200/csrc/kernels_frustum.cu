@@ -159,10 +159,12 @@ __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, c
             default: extreme_step<7>(q, b, pm, ns); break;
             }
             if (i == 1 || i == 3) {
-                bool open = false;
+                // every chunk of the warp rejected already?  (slots past the end of the list hold chunk (0, 0, 0): they
+                // can only keep a tail warp going, never change a result)
+                float open = pm[0];
 #pragma unroll
-                for (int c = 0; c < C; ++c) open |= ((live >> c) & 1u) && !(pm[c] < 0.0f);
-                if (!__any_sync(VX_FULL, open)) return 0;        // every chunk of the warp is rejected already
+                for (int c = 1; c < C; ++c) open = fmaxf(open, pm[c]);
+                if (!__any_sync(VX_FULL, !(open < 0.0f))) return 0;
             }
         }
         todo = 0;

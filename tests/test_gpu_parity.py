@@ -657,6 +657,20 @@ def test_short_list_path_pinned_and_pageable_outputs(ctx, vox, oracle):
         pk = ctx.gen_mesh_packed(coords, nbr_mask=masks)
         pk2 = ctx.gen_mesh_packed(coords, nbr_mask=masks, out=pinned.view(np.uint32))
         assert pk.total == a.total and np.array_equal(pk.instances, pk2.instances)
+    # a pageable list whose instances do not fit the lane's pinned staging buffer (caves: ~50 k quads per chunk, 3 chunks
+    # = 10 MB > 8 MB) falls back to the arena: same bytes as the zero-copy form
+    caves = vox.default_noise_params(freq=0.9, octaves=1)
+    c3 = _grid(2, -1, 3, 1)
+    pa = ctx.gen_mesh(c3, params=caves, nbr_mask=np.full(3, 15, np.uint8))
+    pb = ctx.gen_mesh(c3, params=caves, nbr_mask=np.full(3, 15, np.uint8), out=pinned.view(np.uint8))
+    assert pa.total == pb.total and pa.total * 68 > (8 << 20)
+    assert pa.counts.tolist() == pb.counts.tolist() and pa.instances.tobytes() == pb.instances.tobytes()
+    # pageable destination one quad short: error, nothing written
+    one = ctx.gen_mesh(_grid(0, 0, 1, 1))
+    short = np.full((one.total - 1) * 68 + 64, 0xCD, np.uint8)
+    with pytest.raises(vox.VoxError) as e:
+        ctx.gen_mesh(_grid(0, 0, 1, 1), out=short[:(one.total - 1) * 68])
+    assert e.value.code == vox._lib.VX_ERR_CAPACITY and (short == 0xCD).all()
     # capacity too small: error, counts still valid, nothing written past the buffer
     small = vox.PinnedBuffer(100 * 68)
     guard = small.view(np.uint8)

@@ -87,6 +87,7 @@ constexpr size_t kSliceBytes = size_t(256) << 20;                      // stagin
 constexpr size_t kMaxLanes = 8;                                        // concurrent short-list calls per context
 constexpr size_t kShortList = 32;                                      // lists up to this long take the one-sync path
 constexpr size_t kStageBytes = 4096;                                   // >= kShortList * (12 + 1 + 4 + 8) + 8 + 16
+constexpr size_t kHostInstBytes = size_t(8) << 20;                     // pinned instance staging of the short-list path
 
 struct Dev {
     int id = 0;
@@ -98,6 +99,7 @@ struct Dev {
         inst[2], planes, vis, bits, mesh_mask;
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
+    unsigned char *h_inst = nullptr;    // pinned instance staging for pageable callers of that path (kHostInstBytes, on demand)
     vx_counter launches{0};
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
@@ -373,6 +375,7 @@ void destroy_dev(Dev &d)
         b->release();
     if (d.h_small) cudaFreeHost(d.h_small);
     if (d.h_stage) cudaFreeHost(d.h_stage);
+    if (d.h_inst) cudaFreeHost(d.h_inst);
     for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
     for (auto &ev : d.free_events) {
         cudaEventDestroy(ev.first);
@@ -1039,7 +1042,7 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
     // where the instances go: straight into a pinned caller buffer, else the arena
     void *dev_out = nullptr;
     size_t dev_cap = 0;
-    bool direct = false;
+    bool direct = false, staged = false;
     if (instances) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, instances) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
@@ -1048,11 +1051,28 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
             direct = true;
         } else {
             cudaGetLastError();                       // a pageable pointer is not an error here
-            // a lane's arena only has to hold this list (n <= kShortList chunks)
-            const size_t arena = std::min(kArenaBytes, n * (size_t)VX_MAX_QUADS_PER_CHUNK * rec);
-            CK(d.inst[0].ensure(arena));
-            dev_out = d.inst[0].p;
-            dev_cap = std::min(capacity, arena / rec);
+            // Pageable destination: a cudaMemcpy into it would go through the driver's own staging, one caller at
+            // a time.  The emit writes into this lane's pinned buffer over PCIe instead and the CALLING thread copies
+            // from there (pool threads copy in parallel); a list that does not fit falls back to the arena below.
+            // (terrain has at most ~8 k quads per chunk: longer lists would overflow the buffer and emit twice)
+            const bool fits = n * (size_t)8192 * rec <= kHostInstBytes;
+            if (fits && !d.h_inst && cudaHostAlloc((void **)&d.h_inst, kHostInstBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                d.h_inst = nullptr;
+            }
+            void *dp = nullptr;
+            if (fits && d.h_inst && cudaHostGetDevicePointer(&dp, d.h_inst, 0) == cudaSuccess) {
+                dev_out = dp;
+                dev_cap = std::min(capacity, kHostInstBytes / rec);
+                staged = true;
+            } else {
+                cudaGetLastError();
+                // a lane's arena only has to hold this list (n <= kShortList chunks)
+                const size_t arena = std::min(kArenaBytes, n * (size_t)VX_MAX_QUADS_PER_CHUNK * rec);
+                CK(d.inst[0].ensure(arena));
+                dev_out = d.inst[0].p;
+                dev_cap = std::min(capacity, arena / rec);
+            }
         }
         vx_mesh_args m = emit_args(d, d.coords.as<int32_t>(), nullptr, nullptr, d_cnt, d_off, nn);
         m.out = static_cast<vx_instance *>(dev_out);
@@ -1081,7 +1101,9 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
         RET(dev_stream_instances(d, m, offsets, nn, instances, packed));
         return sync_dev(d);
     }
-    if (!direct && total) {
+    if (staged) {
+        std::memcpy(instances, d.h_inst, total * rec);
+    } else if (!direct && total) {
         CK(cudaMemcpyAsync(instances, dev_out, total * rec, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }

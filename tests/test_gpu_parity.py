@@ -137,6 +137,50 @@ def test_mesh_edge_cases(ctx, vox):
         ctx.fill([(0, 0, 0)], params=vox.default_noise_params(octaves=0))
 
 
+def test_mesh_short_lists_one_sync_path(ctx, vox, oracle):
+    """vx_mesh lists of up to 32 chunks (Chunk::create_mesh: the chunk and its four neighbours, chunk.rs:48-57) go up
+    in one pinned copy and come back after one synchronisation: into pageable memory through the lane's pinned staging,
+    into a pinned caller buffer directly, count-only, with explicit wiring + mesh mask, and past the staging size."""
+    rng = np.random.default_rng(77)
+    pinned = vox.PinnedBuffer(5 * 98304 * 68)
+    for n, p_solid in ((1, 0.5), (5, 0.3), (5, 0.7), (32, 0.05)):
+        coords = np.array([(i % 3 - 1, 0, i // 3) for i in range(n)], np.int32)
+        blocks = np.where(rng.random((n, 32768)) < p_solid, rng.integers(0, 2, (n, 32768)), 2).astype(np.uint8)
+        nbr = rng.integers(-1, n, size=(n, 4)).astype(np.int32)
+        mask = (rng.random(n) < 0.6).astype(np.uint8)
+        mask[0] = 1
+        want = oracle.mesh_batch(coords, blocks, nbr)
+        keep = np.concatenate([np.arange(want["offsets"][i], want["offsets"][i + 1]) for i in range(n) if mask[i]]).astype(np.int64)
+        a = ctx.mesh(coords, blocks, nbr_idx=nbr, mesh_mask=mask)                          # pageable
+        assert a.counts.tolist() == [int(c) if mask[i] else 0 for i, c in enumerate(want["counts"])]
+        assert _canon(a.instances).tobytes() == _canon(want["instances"][keep]).tobytes()
+        if a.total * 68 <= 5 * 98304 * 68:
+            b = ctx.mesh(coords, blocks, nbr_idx=nbr, mesh_mask=mask, out=pinned.view(np.uint8))   # pinned: zero-copy emit
+            assert b.counts.tolist() == a.counts.tolist() and b.instances.tobytes() == a.instances.tobytes()
+        c = ctx.mesh(coords, blocks, nbr_idx=nbr, mesh_mask=mask, instances=False)          # count only
+        assert c.counts.tolist() == a.counts.tolist() and c.total == a.total
+        by_coord = ctx.mesh(coords, blocks)                                                 # neighbours by coordinate
+        assert by_coord.total > 0
+    # the reference's create_mesh shape: the chunk plus four neighbour grids, only the chunk meshed
+    c5 = np.array([(0, 0, 0), (-1, 0, 0), (1, 0, 0), (0, 0, -1), (0, 0, 1)], np.int32)
+    cubes = np.stack([oracle.generate_terrain(c) for c in c5])
+    wiring = np.full((5, 4), -1, np.int32)
+    wiring[0] = (1, 2, 3, 4)
+    got = ctx.mesh(c5, cubes, nbr_idx=wiring, mesh_mask=[1, 0, 0, 0, 0])
+    want = oracle.create_mesh(c5[0], cubes[0], [cubes[1], cubes[2], cubes[3], cubes[4]])
+    assert got.counts.tolist() == [len(want), 0, 0, 0, 0]
+    assert _canon(got.instances).tobytes() == _canon(want).tobytes()
+    # out-of-range wiring is rejected before anything is enqueued; bad block ids are reported
+    with pytest.raises(vox.VoxError) as e:
+        ctx.mesh(c5, cubes, nbr_idx=np.full((5, 4), 5, np.int32))
+    assert e.value.code == vox._lib.VX_ERR_BAD_ARG
+    bad = cubes.copy()
+    bad[3, 5] = 7
+    with pytest.raises(vox.VoxError) as e:
+        ctx.mesh(c5, bad, nbr_idx=wiring)
+    assert e.value.code == vox._lib.VX_ERR_BAD_BLOCK
+
+
 def _grid(x0, z0, nx, nz, y=0):
     return np.array([(x, y, z) for z in range(z0, z0 + nz) for x in range(x0, x0 + nx)], np.int32)
 

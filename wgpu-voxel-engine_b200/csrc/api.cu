@@ -88,6 +88,7 @@ constexpr size_t kMaxLanes = 8;                                        // concur
 constexpr size_t kShortList = 32;                                      // lists up to this long take the one-sync path
 constexpr size_t kStageBytes = 4096;                                   // >= kShortList * (12 + 1 + 4 + 8) + 8 + 16
 constexpr size_t kHostInstBytes = size_t(8) << 20;                     // pinned instance staging of the short-list path
+constexpr size_t kHostUpBytes = kShortList * (VX_VOXELS + 12 + 16 + 1) + 64;   // blocks, coords, nbr_idx, mesh_mask of a short list
 
 struct Dev {
     int id = 0;
@@ -100,6 +101,7 @@ struct Dev {
     uint32_t *h_small = nullptr;   // pinned mirror of `small`
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
     unsigned char *h_inst = nullptr;    // pinned instance staging for pageable callers of that path (kHostInstBytes, on demand)
+    unsigned char *h_up = nullptr;      // pinned upload staging of short vx_mesh lists (kHostUpBytes, on demand)
     vx_counter launches{0};
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
@@ -376,6 +378,7 @@ void destroy_dev(Dev &d)
     if (d.h_small) cudaFreeHost(d.h_small);
     if (d.h_stage) cudaFreeHost(d.h_stage);
     if (d.h_inst) cudaFreeHost(d.h_inst);
+    if (d.h_up) cudaFreeHost(d.h_up);
     for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
     for (auto &ev : d.free_events) {
         cudaEventDestroy(ev.first);
@@ -860,6 +863,96 @@ static int mesh_multi(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_
     });
 }
 
+// Short lists (Chunk::create_mesh of the reference: the chunk and its four neighbours, chunk.rs:48-57): the same
+// one-synchronisation shape as gen_mesh_short.  Blocks, coordinates, neighbour wiring and mask go up in ONE copy from
+// pinned staging (a copy from pageable caller memory would go through the driver's own staging, one caller at a
+// time); the emit is launched speculatively behind the count into the caller's pinned buffer or the lane's pinned
+// staging; offsets, counts and the status word come back in one copy.
+static int mesh_short(Dev &d, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
+                      const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, unsigned char *instances,
+                      size_t capacity, uint64_t *total_out)
+{
+    const size_t rec = sizeof(vx_instance);
+    const uint32_t nn = (uint32_t)n;
+    CK(cudaSetDevice(d.id));
+    cudaStream_t s = d.stream;
+    if (!d.h_up) CK(cudaHostAlloc((void **)&d.h_up, kHostUpBytes, cudaHostAllocPortable));
+    // upload block: [blocks 32768 n][coords 12 n][nbr_idx 16 n][mesh_mask n]
+    const size_t o_coords = n * VX_VOXELS, o_nbr = o_coords + 12 * n, o_mask = o_nbr + (nbr_idx ? 16 * n : 0);
+    const size_t up = o_mask + (mesh_mask ? n : 0);
+    CK(d.blocks.ensure(up));
+    std::memcpy(d.h_up, blocks, n * VX_VOXELS);
+    std::memcpy(d.h_up + o_coords, coords, 12 * n);
+    if (nbr_idx) std::memcpy(d.h_up + o_nbr, nbr_idx, 16 * n);
+    if (mesh_mask) std::memcpy(d.h_up + o_mask, mesh_mask, n);
+    CK(cudaMemcpyAsync(d.blocks.p, d.h_up, up, cudaMemcpyHostToDevice, s));
+    const unsigned char *base = d.blocks.as<unsigned char>();
+    const int32_t *d_coords = reinterpret_cast<const int32_t *>(base + o_coords);
+    const int32_t *d_nbr_idx = nbr_idx ? reinterpret_cast<const int32_t *>(base + o_nbr) : nullptr;
+    const uint8_t *d_mm = mesh_mask ? base + o_mask : nullptr;
+    // download block on the device: [offsets 8 (n + 1)][counts 4 n]
+    const size_t off_bytes = 8 * (n + 1), down = off_bytes + 4 * n;
+    CK(d.offsets.ensure(down));
+    uint64_t *d_off = d.offsets.as<uint64_t>();
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d.offsets.as<unsigned char>() + off_bytes);
+    CK(cudaMemsetAsync(d.st(), 0, 4, s));
+    RET(mesh_prepare(d, s, d_coords, nn, base, d_nbr_idx, d_cnt, d_off, d_mm, d.st()));
+    void *dev_out = nullptr;
+    size_t dev_cap = 0;
+    bool staged = false;
+    if (instances) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, instances) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            dev_out = at.devicePointer;               // pinned caller buffer: the emit writes it directly
+            dev_cap = capacity;
+        } else {
+            cudaGetLastError();                       // a pageable pointer is not an error here
+            if (!d.h_inst && cudaHostAlloc((void **)&d.h_inst, kHostInstBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                d.h_inst = nullptr;
+            }
+            void *dp = nullptr;
+            if (d.h_inst && cudaHostGetDevicePointer(&dp, d.h_inst, 0) == cudaSuccess) {
+                dev_out = dp;
+                dev_cap = std::min(capacity, kHostInstBytes / rec);
+                staged = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (dev_out) {
+            vx_mesh_args m = emit_args(d, d_coords, d.typ.as<uint32_t>(), d_mm, d_cnt, d_off, nn);
+            m.out = static_cast<vx_instance *>(dev_out);
+            m.capacity = dev_cap;
+            m.status = d.st();
+            TIMED(d, s, VX_K_EMIT, vx_launch_mesh_emit(m, nn, s, &d.launches));
+        }
+    }
+    unsigned char *h_down = d.h_stage + 2048;
+    CK(cudaMemcpyAsync(h_down, d_off, down, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_down + down, d.st(), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));                     // the one wait
+    uint32_t st = 0;
+    std::memcpy(&st, h_down + down, 4);
+    std::memcpy(offsets, h_down, off_bytes);
+    std::memcpy(counts, h_down + off_bytes, 4 * n);
+    if (st & VX_ST_BAD_BLOCK)
+        return fail(VX_ERR_BAD_BLOCK, "blocks contain an id outside {0 GRASS, 1 DIRT, 2 AIR} (cube.rs:16-21)");
+    const uint64_t total = offsets[n];
+    if (total_out) *total_out = total;
+    if (!instances) return VX_OK;
+    if (total > capacity)
+        return fail(VX_ERR_CAPACITY, "instance capacity %zu < %llu quads", capacity, (unsigned long long)total);
+    if (!dev_out || (st & VX_ST_OVERFLOW)) {
+        // does not fit the staging buffer the speculative emit was given: sliced path through the arena
+        vx_mesh_args m = emit_args(d, d_coords, d.typ.as<uint32_t>(), d_mm, d_cnt, d_off, nn);
+        RET(dev_stream_instances(d, m, offsets, nn, instances));
+        return sync_dev(d);
+    }
+    if (staged) std::memcpy(instances, d.h_inst, total * rec);
+    return VX_OK;
+}
+
 int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks, const int32_t *nbr_idx,
             const uint8_t *mesh_mask, uint32_t *counts, uint64_t *offsets, vx_instance *instances, size_t capacity,
             uint64_t *total_out)
@@ -878,6 +971,9 @@ int vx_mesh(vx_ctx *ctx, const int32_t *coords, size_t n, const uint8_t *blocks,
     DevGuard guard(ctx, n);
     if (!guard.d) return cuda_fail(guard.err, "lane setup", __LINE__);
     Dev &d = *guard.d;
+    if (n <= kShortList)
+        return mesh_short(d, coords, n, blocks, nbr_idx, mesh_mask, counts, offsets,
+                          reinterpret_cast<unsigned char *>(instances), capacity, total_out);
     CK(cudaSetDevice(d.id));
     cudaStream_t s = d.stream;
     const uint32_t nn = (uint32_t)n;

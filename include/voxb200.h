@@ -93,7 +93,8 @@ const char *vx_last_error(void);
 int vx_device_count(void);
 /* devices == NULL: use n_devices devices starting at 0 (n_devices <= 0: all).
  * With several devices every batch call shards its list by contiguous index
- * ranges, one stream per GPU, no inter-GPU traffic (halo slabs are recomputed). */
+ * ranges, one stream per GPU, no inter-GPU traffic (halo slabs are recomputed).
+ * A device may be named more than once: every entry is a slot with its own streams and scratch. */
 int vx_create(const int *devices, int n_devices, vx_ctx **out);
 void vx_destroy(vx_ctx *ctx);
 int vx_num_devices(const vx_ctx *ctx);

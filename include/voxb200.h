@@ -22,6 +22,11 @@
  *     buffers and streams on the context's first GPU) and run concurrently -- a ninth concurrent caller
  *     waits for a lane.  vx_sync covers the context's own streams, not the lanes (a lane call has
  *     finished when it returns).  Use one context per GPU, or one multi-GPU context.
+ *   - host output buffers may be ordinary pageable memory (a Vec, a numpy array) or pinned memory from
+ *     vx_host_alloc.  Pinned buffers are written at link speed (~50 GB/s); large downloads into pageable
+ *     memory go through the library's own pinned bounce buffers and a few copy threads (default: half
+ *     the hardware threads, at most 8; environment variable VX_COPY_THREADS overrides), 10-25 GB/s
+ *     depending on whether the pages have been touched before.
  *   - chunk edge is fixed at 32 (world.rs:21); voxel index inside a chunk is
  *     idx = x + 32*z + 1024*y (chunk.rs:38,70); chunk -> world is a wrapping
  *     i32 multiply by 32 (coordinate.rs:60-65, release-build semantics).

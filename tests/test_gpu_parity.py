@@ -137,6 +137,29 @@ def test_mesh_edge_cases(ctx, vox):
         ctx.fill([(0, 0, 0)], params=vox.default_noise_params(octaves=0))
 
 
+def test_large_downloads_into_pageable_memory_equal_pinned(ctx, vox):
+    """Downloads of 1 MB and more into pageable caller memory go through the library's pinned bounce buffers and copy
+    threads (4 MB pieces): instance streams, blocks, noise and occupancy equal what lands in pinned buffers, for sizes
+    below, at and across the piece boundaries, from fresh and from reused destinations."""
+    for n_side in ((6, 6), (9, 9), (20, 13)):
+        coords = _grid(-4, 2, *n_side)
+        n = len(coords)
+        pin = vox.PinnedBuffer(n * 8192 * 68)
+        a = ctx.gen_mesh(coords, blocks=True)                               # fresh numpy destinations
+        b = ctx.gen_mesh(coords, out=pin.view(np.uint8))
+        assert a.total == b.total and a.total * 68 > (1 << 20)
+        assert np.array_equal(a.counts, b.counts) and a.instances.tobytes() == b.instances.tobytes()
+        reuse = np.empty(a.total * 68 + 4096, np.uint8)
+        reuse[:] = 0x5A
+        c = ctx.gen_mesh(coords, out=reuse[:a.total * 68])                  # touched destination, exact capacity
+        assert c.instances.tobytes() == a.instances.tobytes() and (reuse[a.total * 68:] == 0x5A).all()
+        f = ctx.fill(coords, blocks=True, noise=True, occupancy=True)
+        assert np.array_equal(f["blocks"], a.blocks)
+        small = ctx.fill(coords[:3], blocks=True, noise=True, occupancy=True)      # below the bounce threshold
+        assert np.array_equal(f["noise"][:3].view(np.uint32), small["noise"].view(np.uint32))
+        assert np.array_equal(f["occupancy"][:3], small["occupancy"]) and np.array_equal(f["blocks"][:3], small["blocks"])
+
+
 def test_mesh_short_lists_one_sync_path(ctx, vox, oracle):
     """vx_mesh lists of up to 32 chunks (Chunk::create_mesh: the chunk and its four neighbours, chunk.rs:48-57) go up
     in one pinned copy and come back after one synchronisation: into pageable memory through the lane's pinned staging,

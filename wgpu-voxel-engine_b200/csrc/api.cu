@@ -88,7 +88,80 @@ constexpr size_t kMaxLanes = 8;                                        // concur
 constexpr size_t kShortList = 32;                                      // lists up to this long take the one-sync path
 constexpr size_t kStageBytes = 4096;                                   // >= kShortList * (12 + 1 + 4 + 8) + 8 + 16
 constexpr size_t kHostInstBytes = size_t(8) << 20;                     // pinned instance staging of the short-list path
+// pinned bounce buffers (two) towards pageable memory, and the threads that copy out of them (default: half the
+// host's hardware threads, at most 8).  Environment: VX_COPY_THREADS (documented in voxb200.h), VX_BOUNCE_KB (A/B aid).
+// Measured on a 16-core host, one call of 1024 chunks = 319 MB into FRESH pageable memory: 2.1 GB/s with
+// cudaMemcpyAsync straight into it, 2.2 / 7.4 / 12.1 / 15.6 GB/s through 4 MB bounce buffers with 1 / 4 / 8 / 16 threads;
+// into already-touched pageable memory 16.7 -> 24-28 GB/s; into pinned memory 48-52 GB/s either way.
+static const size_t kBounceBytes = [] { const char *e = getenv("VX_BOUNCE_KB"); return (e ? (size_t)atoi(e) : size_t(4096)) << 10; }();
+static const unsigned kCopyThreads = [] { const char *e = getenv("VX_COPY_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
+constexpr size_t kBounceMin = size_t(1) << 20;                         // smaller copies go straight through cudaMemcpyAsync
 constexpr size_t kHostUpBytes = kShortList * (VX_VOXELS + 12 + 16 + 1) + 64;   // blocks, coords, nbr_idx, mesh_mask of a short list
+
+// A few helper threads that copy one large block between host buffers in parallel.  A download into PAGEABLE caller
+// memory (a Rust Vec, a numpy array) is what the reference's call sites hand over; cudaMemcpy into it runs at
+// ~2 GB/s when the pages have never been touched (a fresh allocation) because the driver faults and pins them one
+// by one.  The library instead downloads into its own pinned bounce buffers at link speed and copies from there
+// with these threads, so the first-touch page faults of the destination are taken in parallel.
+class ParallelCopier {
+    struct Job { unsigned char *dst; const unsigned char *src; size_t n; };
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> q_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+    void run()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+            if (q_.empty()) return;
+            const Job j = q_.front();
+            q_.pop_front();
+            lk.unlock();
+            std::memcpy(j.dst, j.src, j.n);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+
+public:
+    explicit ParallelCopier(unsigned helpers)
+    {
+        for (unsigned i = 0; i < helpers; ++i) th_.emplace_back([this] { run(); });
+    }
+    ~ParallelCopier()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // copies n bytes; returns when all of them are in dst (the caller copies a share itself)
+    void copy(void *dst_v, const void *src_v, size_t n)
+    {
+        unsigned char *dst = static_cast<unsigned char *>(dst_v);
+        const unsigned char *src = static_cast<const unsigned char *>(src_v);
+        const size_t parts = th_.size() + 1;
+        size_t share = (n / parts + 4095) & ~size_t(4095);          // whole pages per thread
+        if (th_.empty() || n < (size_t(256) << 10)) share = n;
+        size_t done = std::min(share, n);                            // [0, done) is the caller's own share
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t o = done; o < n; o += share) {
+                q_.push_back(Job{dst + o, src + o, std::min(share, n - o)});
+                ++pending_;
+            }
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, done);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
 
 struct Dev {
     int id = 0;
@@ -102,6 +175,9 @@ struct Dev {
     unsigned char *h_stage = nullptr;   // pinned up/download staging of the short-list path (kStageBytes)
     unsigned char *h_inst = nullptr;    // pinned instance staging for pageable callers of that path (kHostInstBytes, on demand)
     unsigned char *h_up = nullptr;      // pinned upload staging of short vx_mesh lists (kHostUpBytes, on demand)
+    unsigned char *h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers towards pageable destinations (on demand)
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    std::unique_ptr<ParallelCopier> copier;            // ... and the threads that copy out of them (on demand)
     vx_counter launches{0};
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
@@ -289,6 +365,62 @@ vx_mesh_args emit_args(const Dev &d, const int32_t *d_coords, const uint32_t *ty
     return m;
 }
 
+// true for memory cudaMemcpyAsync can reach without the driver's pageable staging (pinned / registered / managed)
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type != cudaMemoryTypeUnregistered;
+}
+
+// Device -> PAGEABLE host memory: pieces of kBounceBytes go through two pinned bounce buffers on stream s while the
+// copier threads move the previous piece to its destination.  Returns when all bytes are in dst.
+int d2h_pageable(Dev &d, cudaStream_t s, void *dst_v, const void *src_v, size_t bytes)
+{
+    unsigned char *dst = static_cast<unsigned char *>(dst_v);
+    const unsigned char *src = static_cast<const unsigned char *>(src_v);
+    for (int b = 0; b < 2; ++b) {
+        if (!d.h_bounce[b]) CK(cudaHostAlloc((void **)&d.h_bounce[b], kBounceBytes, cudaHostAllocPortable));
+        if (!d.bounce_ev[b]) CK(cudaEventCreateWithFlags(&d.bounce_ev[b], cudaEventDisableTiming));
+    }
+    if (!d.copier) {
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        d.copier.reset(new ParallelCopier((kCopyThreads ? kCopyThreads : std::min(8u, hw / 2)) - 1));
+    }
+    size_t issued = 0, copied = 0;
+    int k = 0;
+    while (copied < bytes) {
+        if (issued < bytes) {
+            const size_t len = std::min(kBounceBytes, bytes - issued);
+            CK(cudaMemcpyAsync(d.h_bounce[k & 1], src + issued, len, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(d.bounce_ev[k & 1], s));
+            issued += len;
+            ++k;
+        }
+        // the piece before the one just issued (or the last one) is complete or about to be: move it out
+        if (issued - copied > kBounceBytes || issued == bytes) {
+            const int b = (int)((copied / kBounceBytes) & 1);
+            const size_t len = std::min(kBounceBytes, bytes - copied);
+            CK(cudaEventSynchronize(d.bounce_ev[b]));
+            d.copier->copy(dst + copied, d.h_bounce[b], len);
+            copied += len;
+        }
+    }
+    return VX_OK;
+}
+
+// device -> host on stream s: asynchronous into pinned (or small) destinations, through the bounce buffers -- and then
+// complete on return -- into large pageable ones
+int d2h_any(Dev &d, cudaStream_t s, void *dst, const void *src, size_t bytes)
+{
+    if (bytes >= kBounceMin && !host_is_pinned(dst)) return d2h_pageable(d, s, dst, src, bytes);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    return VX_OK;
+}
+
 // Stream the instances of chunks [0, n) (device-local numbering, host copy of
 // the local offsets in h_off) to host memory through the two arenas.
 int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t n, void *h_out_v,
@@ -302,6 +434,16 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
     const size_t need = std::min(kArenaBytes, std::max<size_t>((size_t)h_off[n] * rec, 256));
     CK(d.inst[0].ensure(need));
     if (h_off[n] > kArenaQuads) CK(d.inst[1].ensure(kArenaBytes));
+    // pageable destination: every slice is drained through the pinned bounce buffers (d2h_pageable) AFTER the next
+    // slice's emit has been launched, so the GPU keeps working while the host copies
+    const bool pageable = h_off[n] * rec >= kBounceMin && !host_is_pinned(h_out);
+    struct Pending { int buf; uint64_t first, quads; bool valid; } prev{0, 0, 0, false};
+    auto drain = [&](const Pending &pd) -> int {
+        CK(cudaStreamWaitEvent(d.copy, d.emit_done[pd.buf], 0));
+        RET(d2h_pageable(d, d.copy, h_out + pd.first * rec, d.inst[pd.buf].p, pd.quads * rec));
+        CK(cudaEventRecord(d.d2h_done[pd.buf], d.copy));
+        return VX_OK;
+    };
     uint32_t a = 0;
     int k = 0;
     while (a < n) {
@@ -318,13 +460,19 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
             m.status = d.st();
             TIMED(d, d.stream, VX_K_EMIT, vx_launch_mesh_emit(m, b - a, d.stream, &d.launches));
             CK(cudaEventRecord(d.emit_done[buf], d.stream));
-            CK(cudaStreamWaitEvent(d.copy, d.emit_done[buf], 0));
-            CK(cudaMemcpyAsync(h_out + h_off[a] * rec, d.inst[buf].p, q * rec, cudaMemcpyDeviceToHost, d.copy));
-            CK(cudaEventRecord(d.d2h_done[buf], d.copy));
+            if (pageable) {
+                if (prev.valid) RET(drain(prev));
+                prev = Pending{buf, h_off[a], q, true};
+            } else {
+                CK(cudaStreamWaitEvent(d.copy, d.emit_done[buf], 0));
+                CK(cudaMemcpyAsync(h_out + h_off[a] * rec, d.inst[buf].p, q * rec, cudaMemcpyDeviceToHost, d.copy));
+                CK(cudaEventRecord(d.d2h_done[buf], d.copy));
+            }
             ++k;
         }
         a = b;
     }
+    if (prev.valid) RET(drain(prev));
     return VX_OK;
 }
 
@@ -379,6 +527,11 @@ void destroy_dev(Dev &d)
     if (d.h_stage) cudaFreeHost(d.h_stage);
     if (d.h_inst) cudaFreeHost(d.h_inst);
     if (d.h_up) cudaFreeHost(d.h_up);
+    d.copier.reset();
+    for (int b = 0; b < 2; ++b) {
+        if (d.h_bounce[b]) cudaFreeHost(d.h_bounce[b]);
+        if (d.bounce_ev[b]) cudaEventDestroy(d.bounce_ev[b]);
+    }
     for (auto &st : d.stamps) d.free_events.emplace_back(st.a, st.b);
     for (auto &ev : d.free_events) {
         cudaEventDestroy(ev.first);
@@ -662,15 +815,9 @@ int vx_fill(vx_ctx *ctx, const int32_t *coords, size_t n, const vx_noise_params 
             f.near_zero = near_zero_out ? d.near() : nullptr;
             TIMED(d, d.stream, VX_K_FILL, vx_launch_fill(f, false, d.stream, &d.launches));
             const size_t g = lo + a;
-            if (blocks_out)
-                CK(cudaMemcpyAsync(blocks_out + g * VX_VOXELS, d.blocks.p, c * VX_VOXELS, cudaMemcpyDeviceToHost,
-                                   d.stream));
-            if (noise_out)
-                CK(cudaMemcpyAsync(noise_out + g * VX_VOXELS, d.noise.p, c * VX_VOXELS * 4, cudaMemcpyDeviceToHost,
-                                   d.stream));
-            if (occupancy_out)
-                CK(cudaMemcpyAsync(occupancy_out + g * VX_ROWS, d.occ.p, c * VX_ROWS * 4, cudaMemcpyDeviceToHost,
-                                   d.stream));
+            if (blocks_out) RET(d2h_any(d, d.stream, blocks_out + g * VX_VOXELS, d.blocks.p, c * VX_VOXELS));
+            if (noise_out) RET(d2h_any(d, d.stream, noise_out + g * VX_VOXELS, d.noise.p, c * VX_VOXELS * 4));
+            if (occupancy_out) RET(d2h_any(d, d.stream, occupancy_out + g * VX_ROWS, d.occ.p, c * VX_ROWS * 4));
         }
         if (near_zero_out) CK(cudaMemcpyAsync(d.h_small + 2, d.near(), 8, cudaMemcpyDeviceToHost, d.stream));
     }
@@ -1264,10 +1411,13 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
         loc[di].resize((size_t)c + 1);
         CK(cudaMemcpyAsync(counts + lo[di], d.counts.p, (size_t)c * 4, cudaMemcpyDeviceToHost, d.stream));
         CK(cudaMemcpyAsync(loc[di].data(), d.offsets.p, ((size_t)c + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
-        if (blocks_out)
+        const bool blocks_bounce = blocks_out && (size_t)c * VX_VOXELS >= kBounceMin && !host_is_pinned(blocks_out);
+        if (blocks_out && !blocks_bounce)
             CK(cudaMemcpyAsync(blocks_out + (size_t)lo[di] * VX_VOXELS, d.blocks.p, (size_t)c * VX_VOXELS,
                                cudaMemcpyDeviceToHost, d.stream));
         CK(cudaStreamSynchronize(d.stream));
+        if (blocks_bounce)      // pageable: through the pinned bounce buffers
+            RET(d2h_pageable(d, d.stream, blocks_out + (size_t)lo[di] * VX_VOXELS, d.blocks.p, (size_t)c * VX_VOXELS));
         return VX_OK;
     }));
     uint64_t total = 0;

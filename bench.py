@@ -500,6 +500,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                       "api": "vx_gen_mesh_packed: 4-byte quad records, expanded by the renderer's vertex shader; "
                              "NOT the reference's 68-byte wire format (SURVEY 8f rank 2 extension)"}
 
+    # ---- extra: a bounded sample of the same calls into ordinary PAGEABLE memory (what a Rust Vec is): the library's
+    # pinned bounce buffers + copy threads instead of cudaMemcpyAsync's own pageable path -------------------------
+    pg_calls = min(16, n_calls)
+    pg_out = np.empty(e2e_cap * INSTANCE_BYTES, np.uint8)
+    pg_out[:] = 0                                                # touched once: a reused destination
+    ctxs[0].gen_mesh(band.h_coords[:e2e_nb], nbr_mask=band.h_masks[:e2e_nb], out=pg_out)
+    barrier()
+    t0 = time.perf_counter()
+    pg_quads = 0
+    for i in range(pg_calls):
+        lo = i * e2e_nb
+        pg_quads += ctxs[0].gen_mesh(band.h_coords[lo:lo + e2e_nb], nbr_mask=band.h_masks[lo:lo + e2e_nb], out=pg_out).total
+    pg_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    pg_quads_all = sum_over_ranks(float(pg_quads))
+    e2e_pageable = {"value": world * pg_calls * e2e_nb / pg_s, "unit": "chunks/s",
+                    "d2h_gbs": INSTANCE_BYTES * pg_quads_all / pg_s / 1e9,
+                    "sample": "%d calls of %d chunks per rank into one reused pageable buffer, one host thread per rank "
+                              "(not the headline: `e2e` uses pinned buffers)" % (pg_calls, e2e_nb)}
+    del pg_out
+
     if rank != 0:
         if dist is not None:
             dist.barrier()                                   # rank 0's single-GPU verification pass
@@ -643,6 +664,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "api": "vx_gen_mesh (host buffers, pinned instance buffers), %d chunks per call; two host threads with "
                        "one context each take alternate calls; one full pass over the region" % e2e_nb},
         "e2e_packed_extension": e2e_packed,
+        "e2e_pageable_sample": e2e_pageable,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {

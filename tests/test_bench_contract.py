@@ -57,3 +57,4 @@ def test_own_arm_line():
     assert d["cpu_baseline"]["value"] > 0
     assert d["roofline_mesh"]["steady_state"]["frac"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert 1e4 < d["e2e_pageable_sample"]["value"] < d["value"] and d["e2e_pageable_sample"]["d2h_gbs"] > 1

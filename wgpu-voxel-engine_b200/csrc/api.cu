@@ -129,7 +129,11 @@ class ParallelCopier {
 public:
     explicit ParallelCopier(unsigned helpers)
     {
-        for (unsigned i = 0; i < helpers; ++i) th_.emplace_back([this] { run(); });
+        try {
+            for (unsigned i = 0; i < helpers; ++i) th_.emplace_back([this] { run(); });
+        } catch (...) {
+            // no more threads to be had: the ones that started (possibly none) and the caller do the copying
+        }
     }
     ~ParallelCopier()
     {
@@ -178,6 +182,7 @@ struct Dev {
     unsigned char *h_bounce[2] = {nullptr, nullptr};   // pinned bounce buffers towards pageable destinations (on demand)
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     std::unique_ptr<ParallelCopier> copier;            // ... and the threads that copy out of them (on demand)
+    bool is_lane = false;                              // a scratch lane: its caller thread copies alone
     vx_counter launches{0};
     size_t last_n = 0;             // chunks of the last device batch whose scratch is still valid (vx_emit_again_device)
     bool last_typ = false;         // ... and whether it had a DIRT plane
@@ -387,8 +392,9 @@ int d2h_pageable(Dev &d, cudaStream_t s, void *dst_v, const void *src_v, size_t 
         if (!d.bounce_ev[b]) CK(cudaEventCreateWithFlags(&d.bounce_ev[b], cudaEventDisableTiming));
     }
     if (!d.copier) {
+        // lanes serve pool threads that already run side by side: no helpers there
         const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-        d.copier.reset(new ParallelCopier((kCopyThreads ? kCopyThreads : std::min(8u, hw / 2)) - 1));
+        d.copier.reset(new ParallelCopier(d.is_lane ? 0u : (kCopyThreads ? kCopyThreads : std::min(8u, hw / 2)) - 1));
     }
     size_t issued = 0, copied = 0;
     int k = 0;
@@ -589,6 +595,7 @@ struct LaneLease {
             if (idx >= 0) break;
             if (ctx->lanes.size() < kMaxLanes) {
                 std::unique_ptr<Dev> nd(new Dev());
+                nd->is_lane = true;
                 err = init_dev(*nd, ctx->devs[0].id);
                 if (err != cudaSuccess) {
                     destroy_dev(*nd);

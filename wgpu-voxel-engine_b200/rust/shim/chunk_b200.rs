@@ -93,8 +93,39 @@ pub fn create_mesh_instances(pos: ChunkCoord3D, own: &[u8],
     inst
 }
 
+/// Pinned (page-locked) host memory from `vx_host_alloc`.  A download into it runs at link speed (~50 GB/s); a
+/// download into a fresh `Vec` is bound by the first-touch page faults of the destination (~10 GB/s even with the
+/// library's bounce buffers and copy threads).  One arena per thread, grown on demand.
+struct PinnedArena {
+    ptr: *mut u8,
+    bytes: usize,
+}
+impl PinnedArena {
+    const fn new() -> Self {
+        PinnedArena { ptr: std::ptr::null_mut(), bytes: 0 }
+    }
+    fn ensure(&mut self, bytes: usize) -> *mut u8 {
+        if bytes > self.bytes {
+            if !self.ptr.is_null() {
+                check(unsafe { ffi::vx_host_free(self.ptr as *mut std::ffi::c_void) });
+                self.ptr = std::ptr::null_mut();
+                self.bytes = 0;
+            }
+            let want = bytes + bytes / 4;
+            let mut p: *mut std::ffi::c_void = std::ptr::null_mut();
+            check(unsafe { ffi::vx_host_alloc(&mut p, want) });
+            self.ptr = p as *mut u8;
+            self.bytes = want;
+        }
+        self.ptr
+    }
+}
+thread_local! {
+    static ARENA: std::cell::RefCell<PinnedArena> = std::cell::RefCell::new(PinnedArena::new());
+}
+
 /// The fast path: the worker closure of chunk_builder.rs:80-84 for a whole coordinate list in
-/// one call (noise + meshing on the GPU, instances back through pinned double-buffered D2H).
+/// one call (noise + meshing on the GPU, instances and cube ids straight into this thread's pinned arena).
 /// Returns per-chunk (cube ids, instances).  `nbr_mask[i]` bit k = neighbour k counts as loaded.
 /// ONE pass: the instance buffer is sized from the terrain's typical density and the call is repeated
 /// only if the library answers VX_ERR_CAPACITY (counts, offsets and the exact total are valid then).
@@ -104,29 +135,32 @@ pub fn build_chunks(positions: &[ChunkCoord3D], nbr_mask: Option<&[u8]>) -> Vec<
     let coords: Vec<i32> = positions.iter().flat_map(|p| vec![p.x, p.y, p.z]).collect();
     let mask_ptr = nbr_mask.map_or(std::ptr::null(), |m| m.as_ptr());
     let (mut counts, mut offsets, mut total) = (vec![0u32; n], vec![0u64; n + 1], 0u64);
-    let mut blocks = vec![0u8; n * ffi::VX_VOXELS];
-    // default terrain: ~4.6 k quads per chunk with neighbours, at most ~7.9 k without
-    let mut cap = n * 8192;
-    let mut inst: Vec<InstanceRaw> = Vec::with_capacity(cap);
-    loop {
-        let rc = unsafe {
-            ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
-                             offsets.as_mut_ptr(), inst.as_mut_ptr() as *mut ffi::vx_instance, cap, &mut total,
-                             blocks.as_mut_ptr())
-        };
-        if rc == ffi::VX_ERR_CAPACITY {
-            cap = total as usize; // exact now
-            inst = Vec::with_capacity(cap);
-            continue;
+    ARENA.with(|arena| {
+        let mut arena = arena.borrow_mut();
+        // default terrain: ~4.6 k quads per chunk with neighbours, at most ~7.9 k without
+        let mut cap = n * 8192;
+        loop {
+            let inst_bytes = cap * std::mem::size_of::<InstanceRaw>();
+            let base = arena.ensure(inst_bytes + n * ffi::VX_VOXELS);        // [instances][cube ids]
+            let blk_ptr = unsafe { base.add(inst_bytes) };
+            let rc = unsafe {
+                ffi::vx_gen_mesh(gpu.ctx, coords.as_ptr(), n, std::ptr::null(), mask_ptr, counts.as_mut_ptr(),
+                                 offsets.as_mut_ptr(), base as *mut ffi::vx_instance, cap, &mut total, blk_ptr)
+            };
+            if rc == ffi::VX_ERR_CAPACITY {
+                cap = total as usize; // exact now
+                continue;
+            }
+            check(rc);
+            // the arena is page aligned and InstanceRaw is 17 x 4 bytes, align 4 (renderer/instance.rs:1-6)
+            let inst = unsafe { std::slice::from_raw_parts(base as *const InstanceRaw, total as usize) };
+            let blocks = unsafe { std::slice::from_raw_parts(blk_ptr as *const u8, n * ffi::VX_VOXELS) };
+            return (0..n).map(|i| {
+                (blocks[i * ffi::VX_VOXELS..(i + 1) * ffi::VX_VOXELS].to_vec(),
+                 inst[offsets[i] as usize..offsets[i + 1] as usize].to_vec())
+            }).collect();
         }
-        check(rc);
-        break;
-    }
-    unsafe { inst.set_len(total as usize) };
-    (0..n).map(|i| {
-        (blocks[i * ffi::VX_VOXELS..(i + 1) * ffi::VX_VOXELS].to_vec(),
-         inst[offsets[i] as usize..offsets[i + 1] as usize].to_vec())
-    }).collect()
+    })
 }
 
 /// `Frustum::matrix_to_planes` (frustum_culling.rs:47-85): `m` = `matrix.data.0` flattened.

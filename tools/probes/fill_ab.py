@@ -13,6 +13,9 @@ import torch
 import bench
 import voxb200
 
+if len(sys.argv) > 1:                       # a variant build of the library (tools/probes/build_fill_variants.sh)
+    voxb200._lib.SO_PATH = os.path.abspath(sys.argv[1])
+
 dev = torch.device("cuda", 0)
 ctx = voxb200.Context(devices=[0])
 c, _ = bench.region_rows(-8, 0, 1024)
@@ -39,6 +42,6 @@ occ2 = torch.zeros(m * 1024, dtype=torch.int32, device=dev)
 ctx.fill_device(d_c.data_ptr(), m, occ_ptr=occ2.data_ptr(), noise_ptr=noise.data_ptr(), stream=st.cuda_stream)
 torch.cuda.synchronize()
 same = bool(torch.equal(occ[: m * 1024], occ2))
-print(json.dumps({"variant": os.environ.get("VX_FILL_VARIANT", "default"), "chunks": n, "ms": ms,
+print(json.dumps({"variant": os.path.basename(sys.argv[1]) if len(sys.argv) > 1 else os.environ.get("VX_FILL_VARIANT", "default"), "chunks": n, "ms": ms,
                   "ms_per_1024": ms * 1024 / n, "tflops_equiv": 234 * n * 32768 / (ms * 1e-3) / 1e12,
                   "occupancy_equals_exact_kernel": same}))

@@ -352,11 +352,24 @@ __device__ __noinline__ uint32_t vx_brick_exact_steps(float sx, float sy, float 
 
 // ZB = z blocks per CTA (a CTA owns 32 x 4 ZB x 32 voxels): one index box, one table build and one barrier pair serve
 // ZB times the voxels (the box grows by at most one lattice point along j), and a warp's 8 ZB steps average out the
-// 1 / 2 / 3-evaluation steps better before the final barrier.  Large batches use ZB = 4; short lists keep ZB = 1 so that
-// the grid still fills the machine (dispatch in vx_launch_fill).
+// 1 / 2 / 3-evaluation steps better before the final barrier.  Batches of 8192 chunks and more use ZB = 8 (a whole chunk
+// per CTA: 2.043 -> 2.023 ms per 8192 chunks), of 4096 ZB = 4; short lists keep ZB = 1 so that the grid still fills the
+// machine (dispatch in vx_launch_fill).
+#ifndef VX_FILL_IT_UNROLL
+#define VX_FILL_IT_UNROLL 2
+#endif
+// steps of a column per loop iteration: measured 2.117 / 2.041 / 2.41 / 5.1 ms per 8192 chunks for 1 / 2 / 4 / 8 (the
+// body holds three inlined evaluations, ~16 KB of code per step: past two steps the instruction cache gives out)
+constexpr int kItUnroll = VX_FILL_IT_UNROLL;
+#ifndef VX_FILL_PAIRED_U
+#define VX_FILL_PAIRED_U 0
+#endif
+#ifndef VX_FILL_MIN_CTAS
+#define VX_FILL_MIN_CTAS 4
+#endif
 template <bool WANT_BLOCKS, int ZB>
 // 64 registers -> 4 CTAs (32 warps) per SM: measured 0.326 / 0.301 / 0.288 ms at 2 / 3 / 4 CTAs per SM
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, VX_FILL_MIN_CTAS)
 vx_fill_lattice_kernel(const vx_fill_args a)
 {
     __shared__ __align__(8) uint8_t nib[ZB][32][4][8];    // [z block][y][z & 3][x block] -> 4 occupancy bits
@@ -457,28 +470,32 @@ vx_fill_lattice_kernel(const vx_fill_args a)
                 hxy[o] = VX2(__fadd_rn(fx, fy));
             }
         }
-#pragma unroll 1
-        for (uint32_t it = 0; it < 8u; ++it) {
+        // z[0..5] = (za0, zb0, za1, zb1, za2, zb2): the two voxels' third coordinate per octave
+        auto step_z = [&](uint32_t it, float (&z)[6]) {
             const float ya = __fadd_rn(oz, (float)(4u * it + yy)), yb = __fadd_rn(oz, (float)(4u * it + yy + 2u));
             // scalar multiplies: ptxas would contract a packed product into the packed adds that consume z
-            const float za0 = __fmul_rn(ya, freq), zb0 = __fmul_rn(yb, freq);
-            const float za1 = __fmul_rn(za0, lac), zb1 = __fmul_rn(zb0, lac);
-            const float za2 = __fmul_rn(za1, lac), zb2 = __fmul_rn(zb1, lac);
+            z[0] = __fmul_rn(ya, freq); z[1] = __fmul_rn(yb, freq);
+            z[2] = __fmul_rn(z[0], lac); z[3] = __fmul_rn(z[1], lac);
+            z[4] = __fmul_rn(z[2], lac); z[5] = __fmul_rn(z[3], lac);
+        };
+        auto first_octave = [&](const float (&z)[6]) {
+            return __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(z[4], z[5]), hxy[2], s_og[2], 0), VX2(ka2));
+        };
+        auto finish_step = [&](uint32_t it, const float2 u, const float (&z)[6]) {
             // fused (FMA) evaluation first; a decision is only taken when it clears the error margin
             bool solid_a, solid_b, certain;
-            const float2 u = __fmul2_rn(vxn_simplex3_lattice_x2(hx[2], hy[2], make_float2(za2, zb2), hxy[2], s_og[2], 0), VX2(ka2));
             if (__all_sync(VX_FULL, fminf(fabsf(u.x), fabsf(u.y)) > thr2)) {
                 solid_a = u.x < 0.0f;
                 solid_b = u.y < 0.0f;
                 certain = true;
             } else {
-                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(za1, zb1), hxy[1], s_og[1], 0), VX2(ka1), u);
+                const float2 ut = __ffma2_rn(vxn_simplex3_lattice_x2(hx[1], hy[1], make_float2(z[2], z[3]), hxy[1], s_og[1], 0), VX2(ka1), u);
                 if (__all_sync(VX_FULL, fminf(fabsf(ut.x), fabsf(ut.y)) > thr1)) {
                     solid_a = ut.x < 0.0f;
                     solid_b = ut.y < 0.0f;
                     certain = true;
                 } else {
-                    const float2 r = __ffma2_rn(vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(za0, zb0), hxy[0], s_og[0], 0), VX2(scale), ut);
+                    const float2 r = __ffma2_rn(vxn_simplex3_lattice_x2(hx[0], hy[0], make_float2(z[0], z[1]), hxy[0], s_og[0], 0), VX2(scale), ut);
                     solid_a = r.x < 0.0f;
                     solid_b = r.y < 0.0f;
                     certain = fminf(fabsf(r.x), fabsf(r.y)) > errm;
@@ -489,7 +506,7 @@ vx_fill_lattice_kernel(const vx_fill_args a)
                 // the reference's operation order (separately rounded, r = u + (t + s1))
 #pragma unroll 1
                 for (int e = 0; e < 2; ++e) {
-                    const float q0 = e ? zb0 : za0, q1 = e ? zb1 : za1, q2 = e ? zb2 : za2;
+                    const float q0 = e ? z[1] : z[0], q1 = e ? z[3] : z[2], q2 = e ? z[5] : z[4];
                     const float ue = __fmul_rn(__fmul_rn(vxn_simplex3(hx[2].x, hy[2].x, q2, hxy[2].x, seed), scale), amp2);
                     const float te = __fmul_rn(__fmul_rn(vxn_simplex3(hx[1].x, hy[1].x, q1, hxy[1].x, seed), scale), amp1);
                     const float s1 = __fmul_rn(vxn_simplex3(hx[0].x, hy[0].x, q0, hxy[0].x, seed), scale);
@@ -501,7 +518,27 @@ vx_fill_lattice_kernel(const vx_fill_args a)
             const uint32_t word_a = __ballot_sync(VX_FULL, solid_a), word_b = __ballot_sync(VX_FULL, solid_b);
             if (lane == 2u * it) my_word = word_a;
             if (lane == 2u * it + 1u) my_word = word_b;
+        };
+#if VX_FILL_PAIRED_U
+        // the first octave is evaluated for every step: two steps' evaluations are issued together (independent
+        // instruction streams for the scheduler), then each step is finished on its own
+#pragma unroll 1
+        for (uint32_t it = 0; it < 8u; it += 2u) {
+            float za[6], zb[6];
+            step_z(it, za);
+            step_z(it + 1u, zb);
+            const float2 ua = first_octave(za), ub = first_octave(zb);
+            finish_step(it, ua, za);
+            finish_step(it + 1u, ub, zb);
         }
+#else
+#pragma unroll(kItUnroll)
+        for (uint32_t it = 0; it < 8u; ++it) {
+            float z[6];
+            step_z(it, z);
+            finish_step(it, first_octave(z), z);
+        }
+#endif
         if (lane < 16u) {
             // 8 nibbles (one per (y & 1, z & 3) pair) of this lane's step
 #pragma unroll
@@ -602,8 +639,11 @@ cudaError_t vx_launch_fill(const vx_fill_args &a, bool halo_mode, cudaStream_t s
         if (fmaxf(f0, fmaxf(f1, f2)) <= 0.1f) {
             // z blocks per CTA: as many as still leave >= ~8 waves of CTAs (592 resident on 148 SMs)
             static const int zb_env = [] { const char *e = getenv("VX_FILL_ZB"); return e ? atoi(e) : 0; }();   // A/B aid
-            const int zb = zb_env ? zb_env : (n_items >= 4096u ? 4 : (n_items >= 1024u ? 2 : 1));
-            if (zb == 4) {
+            const int zb = zb_env ? zb_env : (n_items >= 8192u ? 8 : (n_items >= 4096u ? 4 : (n_items >= 1024u ? 2 : 1)));
+            if (zb == 8) {
+                if (a.blocks) vx_fill_lattice_kernel<true, 8><<<n_items, 256, 0, s>>>(b);
+                else vx_fill_lattice_kernel<false, 8><<<n_items, 256, 0, s>>>(b);
+            } else if (zb == 4) {
                 if (a.blocks) vx_fill_lattice_kernel<true, 4><<<n_items * 2u, 256, 0, s>>>(b);
                 else vx_fill_lattice_kernel<false, 4><<<n_items * 2u, 256, 0, s>>>(b);
             } else if (zb == 2) {

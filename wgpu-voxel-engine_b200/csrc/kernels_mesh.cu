@@ -564,6 +564,10 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
 // TYPES: where a quad's block type comes from -- 0: every block is GRASS (the reference's terrain), 1: the caller's
 // DIRT plane (vx_mesh), 2: the DIRT rule of the extension (the voxel above is solid).  A template parameter so that
 // the reference path carries no per-quad test for the other two.
+#ifndef VX_EMIT_TILE_UNROLL
+#define VX_EMIT_TILE_UNROLL 1
+#endif
+constexpr int kEmitTileUnroll = VX_EMIT_TILE_UNROLL;      // A/B aid: tiles per iteration of a warp's tile loop
 template <bool PACKED, int kEmitSplit, int TYPES>
 __global__ void __launch_bounds__(kEmitThreads)
 vx_mesh_emit_kernel(const vx_mesh_args a)
@@ -665,6 +669,7 @@ vx_mesh_emit_kernel(const vx_mesh_args a)
     const uint32_t n_tiles = (count + 31u) >> 5;
     uint32_t it = 0;
 
+#pragma unroll(kEmitTileUnroll)
     for (uint32_t tile = wid + part * kEmitWarps; tile < n_tiles; tile += kEmitWarps * kEmitSplit, ++it) {
         uint32_t *stg = PACKED ? nullptr : s.stage[wid][it % kStageBufs];
         if (!PACKED) {

@@ -275,18 +275,27 @@ __device__ __forceinline__ void stage_chunk(ChunkSmem &s, const vx_mesh_args &a,
     // in-batch x neighbours: transpose bit 31 / bit 0 of their 1024 rows into
     // 32 words (word y, bit z) with one ballot per warp-row-group
     if (nb0 >= 0 || nb1 >= 0) {
+        // all loads of a thread are issued before the first ballot (the count kernel is bound by this latency)
+        constexpr uint32_t kRounds = VX_ROWS / THREADS;
+        static_assert(VX_ROWS % THREADS == 0 && THREADS % 32 == 0, "whole warp-row-groups per round");
         const uint32_t lane = tid & 31u;
-        for (uint32_t r0 = (tid & ~31u); r0 < VX_ROWS; r0 += THREADS) {
-            const uint32_t r = r0 + lane;           // y = r0 / 32, z = lane
+        uint32_t wm[kRounds], wp[kRounds];
+#pragma unroll
+        for (uint32_t k = 0; k < kRounds; ++k) {
+            const uint32_t r = (tid & ~31u) + k * THREADS + lane;          // y = r / 32, z = lane
+            wm[k] = nb0 >= 0 ? __ldg(a.occ + (size_t)nb0 * VX_ROWS + r) : 0u;
+            wp[k] = nb1 >= 0 ? __ldg(a.occ + (size_t)nb1 * VX_ROWS + r) : 0u;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kRounds; ++k) {
+            const uint32_t y = ((tid & ~31u) + k * THREADS) >> 5;
             if (nb0 >= 0) {
-                const uint32_t w = __ldg(a.occ + (size_t)nb0 * VX_ROWS + r);
-                const uint32_t bal = __ballot_sync(VX_FULL, (w >> 31) & 1u);
-                if (lane == 0) s.xm[r0 >> 5] = bal;
+                const uint32_t bal = __ballot_sync(VX_FULL, (wm[k] >> 31) & 1u);
+                if (lane == 0) s.xm[y] = bal;
             }
             if (nb1 >= 0) {
-                const uint32_t w = __ldg(a.occ + (size_t)nb1 * VX_ROWS + r);
-                const uint32_t bal = __ballot_sync(VX_FULL, w & 1u);
-                if (lane == 0) s.xp[r0 >> 5] = bal;
+                const uint32_t bal = __ballot_sync(VX_FULL, wp[k] & 1u);
+                if (lane == 0) s.xp[y] = bal;
             }
         }
     }

@@ -242,8 +242,8 @@ template <int THREADS>
 __device__ __forceinline__ void stage_chunk(ChunkSmem &s, const vx_mesh_args &a, uint32_t m)
 {
     const uint32_t tid = threadIdx.x;
-    const int32_t nb0 = a.nbr[4 * m + 0], nb1 = a.nbr[4 * m + 1];
-    const int32_t nb2 = a.nbr[4 * m + 2], nb3 = a.nbr[4 * m + 3];
+    const int4 nb = __ldg(reinterpret_cast<const int4 *>(a.nbr) + m);      // (the table is the library's own: aligned)
+    const int32_t nb0 = nb.x, nb1 = nb.y, nb2 = nb.z, nb3 = nb.w;
     const uint32_t *own = a.occ + (size_t)m * VX_ROWS;
     // y borders: zero rows = the reference's "always emit" (chunk.rs:216-222,234-240).  Extension: a present
     // vertical neighbour supplies its facing plane (rows (31, z) of the chunk below, rows (0, z) of the one above).
@@ -257,7 +257,12 @@ __device__ __forceinline__ void stage_chunk(ChunkSmem &s, const vx_mesh_args &a,
         s.occ[r] = below;
         s.occ[32 + VX_ROWS + r] = above;
     }
-    for (uint32_t r = tid; r < VX_ROWS; r += THREADS) s.occ[32 + r] = __ldg(own + r);
+    if (THREADS * 4 == VX_ROWS) {
+        // one 128-bit load and store per thread (the occupancy array is the library's own: 4 KiB per chunk, aligned)
+        *reinterpret_cast<uint4 *>(&s.occ[32 + 4 * tid]) = __ldg(reinterpret_cast<const uint4 *>(own) + tid);
+    } else {
+        for (uint32_t r = tid; r < VX_ROWS; r += THREADS) s.occ[32 + r] = __ldg(own + r);
+    }
     if (tid < 32) {
         const uint32_t y = tid;
         uint32_t b = 0, f = 0;

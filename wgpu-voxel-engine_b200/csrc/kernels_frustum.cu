@@ -1,14 +1,17 @@
 // kernels_frustum.cu -- Frustum::contains (frustum_culling.rs:16-40) for
 // n chunk AABBs x F plane sets per launch.
 //
-// One lane owns one chunk and keeps its six AABB coordinates in registers; a
-// CTA covers 256 chunks x up to kFramesPerCta frames whose planes are staged
-// in shared memory (warp-uniform broadcast reads).  The distance is evaluated
-// exactly as the reference does, ((a*x + b*y) + c*z) + d with every product
-// and sum rounded separately (frustum_culling.rs:29-32), and a corner is
-// rejected iff dist < 0 (NaN passes, :33-35).  The result is "any corner
-// inside all six planes" (:37) -- a pure function, so planes may be skipped
-// once no lane of the warp has a live corner.
+// The reference evaluates, per corner and plane, ((a*x + b*y) + c*z) + d with every product and sum rounded
+// separately (:29-32), rejects a corner iff dist < 0 (a NaN distance passes, :33-35) and answers "some corner is
+// inside all six planes" (:37).  Two kernels produce exactly that answer:
+//   vx_frustum_kernel      n chunks x up to 64 plane sets per CTA, planes and their sign classes in shared memory,
+//                          a lane carries four chunks (their 24 corner coordinates) through all frames;
+//   vx_frustum_one_kernel  one plane set per launch (the engine's call shape), four consecutive chunks per thread.
+// Both decide a chunk from the TWO corners per plane that the coefficient signs pick (the distance is a monotone
+// function of each coordinate, see "Extreme-corner classification" below) and run the reference's corner-by-corner
+// test only on chunks that straddle two planes or more -- or on every chunk when a coefficient is NaN, infinite or
+// larger than 2^90, where the ordering argument does not hold.  Planes are skipped once every chunk of a warp is
+// rejected; the side planes go first because they reject the most.
 #include "vx_common.cuh"
 
 namespace {

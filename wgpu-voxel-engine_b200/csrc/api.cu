@@ -7,7 +7,11 @@
 // shard (or outside the list but declared present) is a "halo" whose single
 // border slab is regenerated from the noise on the GPU that needs it.
 // Instances stream back through the two arenas (emit slice k+1 overlaps the
-// D2H of slice k).  There is no CPU compute path in this file.
+// D2H of slice k); into pageable caller memory they go through pinned bounce
+// buffers and copy threads (ParallelCopier, d2h_pageable).  Lists of up to 32
+// chunks -- the reference's one-chunk-per-call shape -- lease a scratch lane
+// and take a one-synchronisation path (gen_mesh_short, mesh_short).
+// There is no CPU compute path in this file: the host only moves bytes.
 #include <algorithm>
 #include <atomic>
 #include <deque>

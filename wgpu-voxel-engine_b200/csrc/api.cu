@@ -97,8 +97,16 @@ constexpr size_t kHostInstBytes = size_t(8) << 20;                     // pinned
 // Measured on a 16-core host, one call of 1024 chunks = 319 MB into FRESH pageable memory: 2.1 GB/s with
 // cudaMemcpyAsync straight into it, 2.2 / 7.4 / 12.1 / 15.6 GB/s through 4 MB bounce buffers with 1 / 4 / 8 / 16 threads;
 // into already-touched pageable memory 16.7 -> 24-28 GB/s; into pinned memory 48-52 GB/s either way.
-static const size_t kBounceBytes = [] { const char *e = getenv("VX_BOUNCE_KB"); return (e ? (size_t)atoi(e) : size_t(4096)) << 10; }();
-static const unsigned kCopyThreads = [] { const char *e = getenv("VX_COPY_THREADS"); return e ? (unsigned)atoi(e) : 0u; }();
+static const size_t kBounceBytes = [] {
+    const char *e = getenv("VX_BOUNCE_KB");
+    const long kb = e ? atol(e) : 4096;
+    return (size_t)std::min(std::max(kb, 64L), 262144L) << 10;      // 64 KB .. 256 MB
+}();
+static const unsigned kCopyThreads = [] {
+    const char *e = getenv("VX_COPY_THREADS");
+    const long t = e ? atol(e) : 0;
+    return (unsigned)std::min(std::max(t, 0L), 64L);                   // 0 = default
+}();
 constexpr size_t kBounceMin = size_t(1) << 20;                         // smaller copies go straight through cudaMemcpyAsync
 constexpr size_t kHostUpBytes = kShortList * (VX_VOXELS + 12 + 16 + 1) + 64;   // blocks, coords, nbr_idx, mesh_mask of a short list
 

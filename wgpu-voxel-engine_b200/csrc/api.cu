@@ -28,6 +28,9 @@
 #include <string>
 #include <vector>
 
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include "vx_common.cuh"
 
 namespace {
@@ -107,7 +110,23 @@ static const unsigned kCopyThreads = [] {
     const long t = e ? atol(e) : 0;
     return (unsigned)std::min(std::max(t, 0L), 64L);                   // 0 = default
 }();
-constexpr size_t kBounceMin = size_t(1) << 20;                         // smaller copies go straight through cudaMemcpyAsync
+// Which downloads into pageable memory take the bounce path (measured on a 16-core host, tools/probes/
+// bounce_threshold_probe.py and pool_probe.cpp): cudaMemcpyAsync's own pageable path does 12-17 GB/s into pages that
+// have been touched before, up to ~16 MB per copy, and collapses to 2-5 GB/s beyond that or when the pages are fresh
+// (never faulted in); the bounce path does 10-16 GB/s into fresh pages and 24-28 GB/s into touched ones, but pays
+// ~100 us of thread wake-ups per piece, which makes it the slower one below ~16 MB of touched memory.  Hence:
+// everything from kBounceAlways up, and from kBounceMin up when the destination's pages are not resident yet.
+// (VX_BOUNCE_MIN_KB / VX_BOUNCE_ALWAYS_KB: A/B aids.)
+static const size_t kBounceMin = [] {
+    const char *e = getenv("VX_BOUNCE_MIN_KB");
+    const long kb = e ? atol(e) : 1024;
+    return (size_t)std::max(kb, 64L) << 10;
+}();
+static const size_t kBounceAlways = [] {
+    const char *e = getenv("VX_BOUNCE_ALWAYS_KB");
+    const long kb = e ? atol(e) : 24576;
+    return (size_t)std::max(kb, 64L) << 10;
+}();
 constexpr size_t kHostUpBytes = kShortList * (VX_VOXELS + 12 + 16 + 1) + 64;   // blocks, coords, nbr_idx, mesh_mask of a short list
 
 // A few helper threads that copy one large block between host buffers in parallel.  A download into PAGEABLE caller
@@ -393,6 +412,31 @@ bool host_is_pinned(const void *p)
     return at.type != cudaMemoryTypeUnregistered;
 }
 
+// true if most of the pages of [p, p + bytes) have never been touched (a fresh allocation): sampled with mincore
+bool host_is_fresh(const void *p, size_t bytes)
+{
+    const long page = sysconf(_SC_PAGESIZE);
+    if (page <= 0 || bytes < (size_t)page * 2) return false;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)(page - 1);
+    const size_t pages = (reinterpret_cast<uintptr_t>(p) + bytes - lo + page - 1) / page;
+    unsigned absent = 0, seen = 0;
+    for (unsigned k = 0; k < 16; ++k) {
+        unsigned char vec = 0;
+        void *addr = reinterpret_cast<void *>(lo + (pages * k / 16) * (size_t)page);
+        if (mincore(addr, (size_t)page, &vec) != 0) continue;      // not mapped the way mincore likes: treat as touched
+        ++seen;
+        if (!(vec & 1u)) ++absent;
+    }
+    return seen >= 8 && absent * 2 > seen;
+}
+
+// does a download of `bytes` into `dst` take the bounce path?
+bool use_bounce(const void *dst, size_t bytes)
+{
+    if (bytes < kBounceMin || host_is_pinned(dst)) return false;
+    return bytes >= kBounceAlways || host_is_fresh(dst, bytes);
+}
+
 // Device -> PAGEABLE host memory: pieces of kBounceBytes go through two pinned bounce buffers on stream s while the
 // copier threads move the previous piece to its destination.  Returns when all bytes are in dst.
 int d2h_pageable(Dev &d, cudaStream_t s, void *dst_v, const void *src_v, size_t bytes)
@@ -434,7 +478,7 @@ int d2h_pageable(Dev &d, cudaStream_t s, void *dst_v, const void *src_v, size_t 
 // complete on return -- into large pageable ones
 int d2h_any(Dev &d, cudaStream_t s, void *dst, const void *src, size_t bytes)
 {
-    if (bytes >= kBounceMin && !host_is_pinned(dst)) return d2h_pageable(d, s, dst, src, bytes);
+    if (use_bounce(dst, bytes)) return d2h_pageable(d, s, dst, src, bytes);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
     return VX_OK;
 }
@@ -454,7 +498,7 @@ int dev_stream_instances(Dev &d, vx_mesh_args m, const uint64_t *h_off, uint32_t
     if (h_off[n] > kArenaQuads) CK(d.inst[1].ensure(kArenaBytes));
     // pageable destination: every slice is drained through the pinned bounce buffers (d2h_pageable) AFTER the next
     // slice's emit has been launched, so the GPU keeps working while the host copies
-    const bool pageable = h_off[n] * rec >= kBounceMin && !host_is_pinned(h_out);
+    const bool pageable = use_bounce(h_out, h_off[n] * rec);
     struct Pending { int buf; uint64_t first, quads; bool valid; } prev{0, 0, 0, false};
     auto drain = [&](const Pending &pd) -> int {
         CK(cudaStreamWaitEvent(d.copy, d.emit_done[pd.buf], 0));
@@ -1346,8 +1390,11 @@ static int gen_mesh_short(Dev &d, const int32_t *coords, size_t n, const vx_nois
     unsigned char *h_down = d.h_stage + 2048;
     CK(cudaMemcpyAsync(h_down, d_off, down, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h_down + down, d.st(), 4, cudaMemcpyDeviceToHost, s));
-    if (blocks_out) CK(cudaMemcpyAsync(blocks_out, d_blocks, n * VX_VOXELS, cudaMemcpyDeviceToHost, s));
+    // cube ids: a few chunks go straight to the caller; more of them into pageable memory go through the bounce buffers
+    const bool blocks_bounce = blocks_out && use_bounce(blocks_out, n * VX_VOXELS);
+    if (blocks_out && !blocks_bounce) CK(cudaMemcpyAsync(blocks_out, d_blocks, n * VX_VOXELS, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));                     // the one wait
+    if (blocks_bounce) RET(d2h_pageable(d, s, blocks_out, d_blocks, n * VX_VOXELS));
     std::memcpy(offsets, h_down, off_bytes);
     std::memcpy(counts, h_down + off_bytes, 4 * n);
     uint32_t st = 0;
@@ -1430,7 +1477,7 @@ static int gen_mesh_host_impl(vx_ctx *ctx, const int32_t *coords, size_t n, cons
         loc[di].resize((size_t)c + 1);
         CK(cudaMemcpyAsync(counts + lo[di], d.counts.p, (size_t)c * 4, cudaMemcpyDeviceToHost, d.stream));
         CK(cudaMemcpyAsync(loc[di].data(), d.offsets.p, ((size_t)c + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
-        const bool blocks_bounce = blocks_out && (size_t)c * VX_VOXELS >= kBounceMin && !host_is_pinned(blocks_out);
+        const bool blocks_bounce = blocks_out && use_bounce(blocks_out + (size_t)lo[di] * VX_VOXELS, (size_t)c * VX_VOXELS);
         if (blocks_out && !blocks_bounce)
             CK(cudaMemcpyAsync(blocks_out + (size_t)lo[di] * VX_VOXELS, d.blocks.p, (size_t)c * VX_VOXELS,
                                cudaMemcpyDeviceToHost, d.stream));

@@ -39,7 +39,7 @@ class TerrainOpts(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile libvoxb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", "Makefile"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "voxb200.h"))
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:

@@ -93,3 +93,23 @@ def test_unusable_plane_sets_are_recognised():
     # where the bound comes from: |coordinate| <= 2^31, so coefficients up to 2^90 keep products and sums finite
     big = f32(2.0 ** 31) * LIM
     assert np.isfinite(((big + big) + big) + LIM)
+
+
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_coef = st.floats(min_value=-float(LIM), max_value=float(LIM), width=32, allow_nan=False, allow_infinity=False)
+_chunk = st.integers(min_value=-(1 << 31), max_value=(1 << 31) - 1)       # any i32: the world coordinate wraps
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(planes=st.lists(_coef, min_size=24, max_size=24), coords=st.lists(st.tuples(_chunk, _chunk, _chunk), min_size=1, max_size=24))
+def test_any_finite_plane_set_and_any_i32_chunk(oracle, planes, coords):
+    """hypothesis: whatever finite coefficients (subnormals, signed zeros, up to 2^90) and whatever i32 chunk coordinates,
+    a chunk the two extreme corners reject is invisible for the reference and a chunk they accept is visible."""
+    pl = np.array(planes, f32).reshape(6, 4)
+    c = np.array(coords, np.int64).astype(np.int32)
+    want = oracle.frustum_cull(pl.reshape(1, 6, 4), c)[0].astype(bool)
+    rejected, inside = classify(pl, c)
+    assert not np.any(rejected & inside)
+    assert not np.any(want[rejected]) and np.all(want[inside])

@@ -16,11 +16,13 @@ f32 = np.float32
 LIM = f32(2.0 ** 90)
 
 
-@pytest.fixture(scope="module")
-def shim(tmp_path_factory):
+@pytest.fixture(scope="module", params=[0, 1], ids=["plane-by-plane", "plane-pairs"])
+def shim(tmp_path_factory, request):
+    # both compile-time forms of the classification loop (VX_FR_PAIR_MIN: two planes join the running minimum at once)
     so = str(tmp_path_factory.mktemp("shim") / "libfrustum_host.so")
     src = os.path.join(ROOT, "tests", "host_shim", "frustum_host.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-DVX_FR_PAIR_MIN=%d" % request.param, "-o", so, src])
     L = C.CDLL(so)
     L.shim_frustum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.shim_corner_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

